@@ -1,0 +1,122 @@
+/*
+ * yfv2.h — C ABI of libyfv2.so, the B200 (sm_100a) implementation of the Yolo-FastestV2 hot path.
+ *
+ * The reference (dog-qiuqiu/Yolo-FastestV2 @ ac2a5e3) has no FFI of its own: its boundary is the
+ * Python import surface.  Each entry point below replaces one reference function; the
+ * Python mirror modules under yolo-fastestv2_b200/{model,utils}/ call these through ctypes and give
+ * the result the reference's return types.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Every function returns 0 on success or a negative
+ *     YFV2_E* code; yfv2_last_error() returns a thread-local message for the last failure.
+ *   - All `float*` / `void*` tensor arguments are DEVICE pointers unless the name ends in `_host`.
+ *   - The caller owns every buffer (inputs, outputs, packed weights, workspace).  The library never
+ *     allocates or frees device memory; the only state is the opaque host-side yfv2_plan.
+ *   - `stream` is a cudaStream_t passed as void* (Python: torch.cuda.current_stream().cuda_stream).
+ *     All launches are asynchronous on it; nothing here synchronises the device, except the
+ *     *_host convenience calls which say so.
+ *   - No C++ exception crosses the ABI.  There is no CPU fallback: without a CUDA device every
+ *     compute entry point returns YFV2_ECUDA.
+ */
+#ifndef YFV2_H_
+#define YFV2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YFV2_OK            0
+#define YFV2_EINVAL       -1   /* bad argument (null pointer, unsupported shape) */
+#define YFV2_ECUDA        -2   /* a CUDA runtime call or launch failed */
+#define YFV2_EUNSUPPORTED -3   /* valid request this build does not implement */
+#define YFV2_ENOMEM       -4   /* host allocation failed / workspace too small */
+
+#define YFV2_ABI_VERSION   1
+
+#if defined(__GNUC__)
+#define YFV2_API __attribute__((visibility("default")))
+#else
+#define YFV2_API
+#endif
+
+/* Number of float tensors yfv2_pack_weights consumes, in reference state_dict order:
+ * 225 parameters (Detector.parameters(), model/detector.py:8-19) and 73 BatchNorm layers. */
+#define YFV2_NUM_PARAMS    225
+#define YFV2_NUM_BN         73
+#define YFV2_NUM_GRADS  243095  /* 80 classes, 3 anchors */
+
+typedef struct yfv2_plan yfv2_plan;
+
+YFV2_API int         yfv2_abi_version(void);
+YFV2_API const char* yfv2_last_error(void);
+
+/* ---- plan -----------------------------------------------------------------------------------------
+ * One plan per (device, N, H, W, A, C, training).  H and W must be multiples of 32
+ * (model/backbone/shufflenetv2.py strides; utils/loss.py:78).  Replaces Detector.__init__'s shape
+ * bookkeeping (model/detector.py:8-19). */
+YFV2_API int yfv2_plan_create(yfv2_plan** plan, int device, int N, int H, int W, int A, int C, int training);
+YFV2_API int yfv2_plan_destroy(yfv2_plan* plan);
+YFV2_API int yfv2_plan_workspace_bytes(const yfv2_plan* plan, size_t* bytes);
+YFV2_API int yfv2_plan_packed_bytes(const yfv2_plan* plan, size_t* bytes);
+/* number of kernels one yfv2_forward / yfv2_detect launches (for bench.py's gpu_launches) */
+YFV2_API int yfv2_plan_forward_launches(const yfv2_plan* plan, int* n);
+
+/* ---- weights ----------------------------------------------------------------------------------------
+ * params:     225 device pointers, Detector.parameters() order (== state_dict order without buffers).
+ * bn_running: 146 device pointers, (running_mean, running_var) for each of the 73 BatchNorm2d in
+ *             state_dict order.  Eval plans fold BN into per-channel scale/shift kept next to the
+ *             transposed conv weights (eps = 1e-5, nn.BatchNorm2d default used by the reference). */
+YFV2_API int yfv2_pack_weights(yfv2_plan* plan, const float* const* params, const float* const* bn_running,
+                      void* packed, void* stream);
+
+/* ---- Detector.forward (model/detector.py:21-31,46-47) ------------------------------------------------
+ * x: [N,3,H,W] fp32 NCHW in [0,1] (BGR).  preds: six dense NCHW tensors
+ * (reg_2 [N,4A,H/16,W/16], obj_2 [N,A,..], cls_2 [N,C,..], reg_3, obj_3, cls_3 at H/32) raw logits. */
+YFV2_API int yfv2_forward(yfv2_plan* plan, const float* x, const void* packed, float* const preds[6],
+                 void* workspace, void* stream);
+/* Same, from uint8 [N,3,H,W]: fuses the `imgs.float() / 255.0` of utils/utils.py:368, test.py:38,
+ * train.py:101 into the stem kernel's load. */
+YFV2_API int yfv2_forward_u8(yfv2_plan* plan, const uint8_t* x, const void* packed, float* const preds[6],
+                    void* workspace, void* stream);
+
+/* ---- handel_preds (utils/utils.py:303-358) -----------------------------------------------------------
+ * anchors_host: 2*A*2 doubles (level-major, cfg["anchors"]).  out: [N, (H/16*W/16 + H/32*W/32)*A, 5+C]
+ * fp32, row (y*w+x)*A+a within a level, stride-16 level first.  img_h is cfg["height"] (the reference
+ * derives ONE stride from it for both axes, utils/utils.py:332). */
+YFV2_API int yfv2_decode(const float* const preds[6], int N, int H, int W, int A, int C,
+                const double* anchors_host, float* out, void* stream);
+
+/* ---- non_max_suppression (utils/utils.py:232-296) + torchvision.ops.nms ------------------------------
+ * dets: [N,M,5+C].  out: [N,max_det,6] rows (x1,y1,x2,y2,conf,cls) by descending conf; counts: [N];
+ * kept_idx (optional, may be NULL): [N,max_det] row index into dets[n].  class_filter: n_filter device
+ * ints or NULL.  Candidates per image are limited to YFV2_NMS_MAX_CAND (the reference's max_nms=30000
+ * branch, utils/utils.py:278-280, cannot trigger below that); larger M returns YFV2_EUNSUPPORTED.
+ * The reference's 1-second wall-clock abort (utils/utils.py:292-294) is not reproduced. */
+#define YFV2_NMS_MAX_CAND 8192
+YFV2_API int yfv2_nms_workspace_bytes(int N, int M, int C, size_t* bytes);
+YFV2_API int yfv2_nms(const float* dets, int N, int M, int C, float conf_thres, double iou_thres,
+             const int* class_filter, int n_filter, int max_det, float max_wh,
+             float* out, int* counts, int* kept_idx, void* workspace, void* stream);
+
+/* Fused decode + NMS straight from the six head tensors (no [N,M,5+C] round trip through HBM);
+ * bit-identical to yfv2_decode followed by yfv2_nms. */
+YFV2_API int yfv2_decode_nms(const float* const preds[6], int N, int H, int W, int A, int C,
+                    const double* anchors_host, float conf_thres, double iou_thres,
+                    const int* class_filter, int n_filter, int max_det, float max_wh,
+                    float* out, int* counts, int* kept_idx, void* workspace, void* stream);
+
+/* ---- whole inference step with HOST buffers (the evaluation() inner loop, utils/utils.py:367-383) ----
+ * x_host: pinned uint8 [N,3,H,W]; out_host: pinned [N,max_det,6]; counts_host: pinned [N].
+ * Copies in, runs forward_u8 + decode_nms, copies out, all on `stream`; returns without synchronising. */
+YFV2_API int yfv2_detect_u8_host(yfv2_plan* plan, const uint8_t* x_host, const void* packed,
+                        const double* anchors_host, float conf_thres, double iou_thres, int max_det,
+                        float* out_host, int* counts_host, void* workspace, void* stream);
+YFV2_API size_t yfv2_detect_workspace_bytes(const yfv2_plan* plan, int max_det);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YFV2_H_ */

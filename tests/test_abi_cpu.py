@@ -1,0 +1,82 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/yfv2.h declares,
+the Python mirror keeps the reference's module tree and config surface, and the product path refuses
+to run without CUDA (no fallback)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import yfv2  # noqa: F401  (registers the package dir)
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "yfv2.h")).read()
+    return sorted(set(re.findall(r"YFV2_API[^;]*?\b(yfv2_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import yfv2_engine
+    lib = yfv2_engine.lib()
+    syms = header_symbols()
+    assert len(syms) >= 16
+    for s in syms:
+        assert hasattr(lib, s), s
+        assert s in yfv2_engine.PROTOTYPES, "ctypes prototype missing for " + s
+    assert lib.yfv2_abi_version() == 1
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    import yfv2_engine
+    lib = yfv2_engine.lib()
+    h = ctypes.c_void_p()
+    assert lib.yfv2_plan_create(ctypes.byref(h), 0, 1, 100, 352, 3, 80, 0) == -1      # H not a multiple of 32
+    assert b"multiples of 32" in lib.yfv2_last_error()
+    assert lib.yfv2_plan_create(ctypes.byref(h), 0, 2, 64, 96, 3, 80, 0) == 0         # plans are host-only objects
+    nb = ctypes.c_size_t()
+    assert lib.yfv2_plan_workspace_bytes(h, ctypes.byref(nb)) == 0 and nb.value > 0
+    assert lib.yfv2_plan_packed_bytes(h, ctypes.byref(nb)) == 0 and nb.value > 243095 * 4
+    n = ctypes.c_int()
+    assert lib.yfv2_plan_forward_launches(h, ctypes.byref(n)) == 0 and n.value == 23
+    assert lib.yfv2_plan_destroy(h) == 0
+
+
+def test_state_dict_matches_reference_keys(golden_dir):
+    import model.detector as det
+    m = det.Detector(80, 3, True)
+    ref = json.load(open(os.path.join(golden_dir, "statedict_keys.json")))
+    got = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert got == ref
+    assert len(list(m.parameters())) == 225 and sum(p.numel() for p in m.parameters()) == 243095
+    m.load_state_dict(synth.make_state_dict(3), strict=True)
+    w = dict(__import__("numpy").load(os.path.join(golden_dir, "modelzoo_weights.npz")))
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)       # test.py:28 contract
+
+
+def test_no_cpu_fallback():
+    import model.detector as det
+    m = det.Detector(80, 3, True).eval()
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        m.backbone(torch.zeros(1, 3, 64, 64))
+
+
+def test_load_datafile(tmp_path):
+    import utils.utils as uu
+    p = tmp_path / "x.data"
+    p.write_text("[name]\nmodel_name=coco\n\n[train-configure]\nepochs=300\nsteps=150,250\nbatch_size=128\n"
+                 "subdivisions=1\nlearning_rate=0.001\n\n[model-configure]\npre_weights=None\nclasses=80\nwidth=352\n"
+                 "height=352\nanchor_num=3\nanchors=12.64,19.39, 37.88,51.48, 55.71,138.31, 126.91,78.23, 131.57,214.55, 279.92,258.87\n"
+                 "\n[data-configure]\ntrain=/a/train.txt\nval=/a/val.txt\nnames=./data/coco.names\nbogus=1\n")
+    cfg = uu.load_datafile(str(p))
+    assert cfg["anchors"] == synth.COCO_ANCHORS and cfg["steps"] == [150.0, 250.0]
+    assert cfg["pre_weights"] == "None" and cfg["classes"] == 80 and cfg["learning_rate"] == 0.001
+    assert (cfg["width"], cfg["height"], cfg["anchor_num"], cfg["batch_size"]) == (352, 352, 3, 128)
+    assert set(cfg) == {"model_name", "epochs", "steps", "batch_size", "subdivisions", "learning_rate", "pre_weights",
+                        "classes", "width", "height", "anchor_num", "anchors", "val", "train", "names"}

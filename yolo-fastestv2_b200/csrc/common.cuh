@@ -1,0 +1,161 @@
+// Shared declarations for libyfv2.so (sm_100a only).
+//
+// Activation storage ("plane pools"): every intermediate tensor of the network lives as separate
+// channel planes, plane(n, c) = base + n*sN + c*sC, each plane a dense H*W fp32 image.  A logical
+// tensor is a list of physical plane ids (ChanTab).  ShuffleNetV2's channel_shuffle / split / concat
+// (reference model/backbone/shufflenetv2.py:48-63) therefore cost nothing: they are edits of the id
+// list done on the host when the plan is built, and the "passthrough" half of a stride-1 block is
+// never read or written at all.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/yfv2.h"
+
+namespace yfv2 {
+
+constexpr int kMaxCh = 288;       // widest logical tensor: cat(up(C3), C2), fpn.py:58
+constexpr float kBnEps = 1e-5f;   // nn.BatchNorm2d default
+
+struct Planes {
+    float* base;
+    long long sN;   // floats between consecutive images
+    long long sC;   // floats between consecutive planes
+    int H, W;
+};
+
+struct ChanTab {
+    unsigned short c[kMaxCh];
+};
+
+__device__ __forceinline__ float* plane_ptr(const Planes& P, int n, int c) {
+    return P.base + (long long)n * P.sN + (long long)c * P.sC;
+}
+
+// ---- error plumbing (host) ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define YFV2_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            yfv2::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return YFV2_ECUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+#define YFV2_LAUNCH_CHECK()                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                 \
+        if (e__ != cudaSuccess) {                                                             \
+            yfv2::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return YFV2_ECUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+// ---- packed weight layouts (floats) ----------------------------------------------------------------
+// PW  (1x1 conv K->N [+BN]):  Wt[K][Np] (Np = N rounded up to 4, zero padded), scale[Np], shift[Np]
+// DW3 (3x3 depthwise + BN):   per channel 12 floats: w[9], scale, shift, 0
+// DW5 (5x5 depthwise + BN):   per channel 28 floats: w[25], scale, shift, 0
+// STEM (3x3 s2 3->24 + BN):   Wt[27][24] (k = c*9+ky*3+kx), scale[24], shift[24]
+__host__ __device__ constexpr int round4(int x) { return (x + 3) & ~3; }
+__host__ __device__ constexpr int pw_pack_floats(int K, int N) { return K * round4(N) + 2 * round4(N); }
+__host__ __device__ constexpr int dw3_pack_floats(int C) { return C * 12; }
+__host__ __device__ constexpr int dw5_pack_floats(int C) { return C * 28; }
+constexpr int kStemPackFloats = 27 * 24 + 48;
+
+// ---- device helpers --------------------------------------------------------------------------------
+// cooperative copy global -> shared, count floats (both 4-byte aligned only)
+__device__ __forceinline__ void copy_to_smem(float* dst, const float* __restrict__ src, int count) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// acc[i][n] += Wt[k][n] * x[i]  for one k; Wt row is N floats in shared memory, read as float4 broadcasts
+template <int N, int PPT>
+__device__ __forceinline__ void fma_row(const float* __restrict__ wrow, const float (&x)[PPT], float (&acc)[PPT][N]) {
+#pragma unroll
+    for (int n4 = 0; n4 < N / 4; ++n4) {
+        const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * n4);
+#pragma unroll
+        for (int i = 0; i < PPT; ++i) {
+            acc[i][4 * n4 + 0] = fmaf(w.x, x[i], acc[i][4 * n4 + 0]);
+            acc[i][4 * n4 + 1] = fmaf(w.y, x[i], acc[i][4 * n4 + 1]);
+            acc[i][4 * n4 + 2] = fmaf(w.z, x[i], acc[i][4 * n4 + 2]);
+            acc[i][4 * n4 + 3] = fmaf(w.w, x[i], acc[i][4 * n4 + 3]);
+        }
+    }
+}
+
+// Stage rows [gr0, gr0+nrows) of the K planes listed in tab into X[k][rr*WS + PAD + x]; WS = W + 2*PAD.
+// Out-of-image rows and the PAD columns are written as zeros (the zero padding of the next conv).
+template <int K, int PAD, int NTHREADS>
+__device__ __forceinline__ void stage_rows(float* __restrict__ X, int RS, int WS, const Planes& P, const ChanTab& tab,
+                                           int n, int gr0, int nrows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = NTHREADS >> 5;
+    const int W = P.W, H = P.H;
+    for (int row = warp; row < K * nrows; row += nwarps) {
+        const int k = row / nrows, rr = row - k * nrows;
+        const int gr = gr0 + rr;
+        float* dst = X + k * RS + rr * WS;
+        if (gr >= 0 && gr < H) {
+            const float* src = plane_ptr(P, n, tab.c[k]) + (long long)gr * W;
+            for (int cc = lane; cc < WS; cc += 32) {
+                const int x = cc - PAD;
+                dst[cc] = (x >= 0 && x < W) ? __ldg(src + x) : 0.f;
+            }
+        } else {
+            for (int cc = lane; cc < WS; cc += 32) dst[cc] = 0.f;
+        }
+    }
+}
+
+int sm_count();
+constexpr size_t kSmemCap = 227 * 1024;
+
+// ---- kernel launchers (defined in the k_*.cu files) ---------------------------------------------------
+struct StemArgs {
+    const void* x;       // [N,3,H,W] fp32 or uint8
+    int is_u8;
+    int N, H, W;         // input dims
+    Planes out;          // 24 planes at H/4 x W/4, ids 0..23
+    const float* wpack;  // STEM layout
+};
+int launch_stem(const StemArgs& a, cudaStream_t s);
+
+struct ShuffleArgs {
+    int K;               // branch width: 24 / 48 / 96
+    int stride;          // 1 or 2
+    int N;
+    Planes in, out;      // stride 1: same pool
+    ChanTab tin;         // stride 1: K main-branch inputs (odd logical channels); stride 2: K inputs
+    ChanTab tout;        // stride 1: K output planes; stride 2: 2K (proj then main)
+    const float* wpack;  // see k_shuffle.cu
+};
+int launch_shuffle(const ShuffleArgs& a, cudaStream_t s);
+size_t shuffle_pack_floats(int K, int stride);
+
+struct FpnArgs {
+    int N;
+    Planes c3;  ChanTab t3;   // 192 planes at H/32
+    Planes c2;  ChanTab t2;   // 96 planes at H/16
+    Planes s3, s2;            // outputs: 72 planes each (ids 0..71)
+    const float* w3;          // PW 192->72
+    const float* w2;          // PW 288->72  (k order: up(C3) 0..191, C2 192..287; fpn.py:58)
+};
+int launch_fpn(const FpnArgs& a, cudaStream_t s);
+
+struct HeadArgs {
+    int N, A, C;
+    Planes s;                 // input 72 planes (S2 or S3)
+    Planes t_cls, t_reg;      // scratch 72 planes each (mid-block activations)
+    const float* w_cls;       // DWConvblock pack (see k_head.cu) for the cls head
+    const float* w_reg;
+    const float* w_out_reg;   // PW 72->4A with bias as shift, scale 1
+    const float* w_out_oc;    // PW 72->(A+C): obj rows first, then cls rows
+    float* reg; float* obj; float* cls;   // dense NCHW outputs for this level
+};
+int launch_heads(const HeadArgs& a, cudaStream_t s);
+size_t head_pack_floats();
+
+}  // namespace yfv2

@@ -1,0 +1,500 @@
+// K6 / K7 — anchor-grid decode and per-image NMS, plus the fused decode+NMS that never writes the
+// [N, M, 5+C] candidate tensor.
+//
+//   decode  <- reference utils/utils.py:298-358  (make_grid + handel_preds)
+//   nms     <- reference utils/utils.py:67-74,232-296 (xywh2xyxy + non_max_suppression) and the greedy
+//              kernel of torchvision.ops.nms that it calls at :286.
+//
+// Bit-exactness contract (tests/test_post_gpu.py): given identical [N,M,5+C] inputs the kept rows and
+// indices equal the reference's bit for bit.  That needs: fp32 products obj*cls with first-max argmax,
+// strict '>' filters, box = xy -/+ wh/2, class offset cls*4096 added in fp32, IoU = inter/(a+b-inter)
+// in fp32 compared as double against the threshold, stable descending order (ties by original row),
+// and no FMA contraction anywhere in that arithmetic — every step uses the __f*_rn intrinsics.
+#include "common.cuh"
+
+namespace yfv2 {
+namespace {
+
+constexpr int NT = 256;
+constexpr int kMaxA = 8;
+constexpr int kCPL = 8;              // classes per lane -> C <= 256
+constexpr int kChunkCells = 32;
+constexpr int kSStride = kChunkCells + 1;
+constexpr int kNmsChunk = 64;
+
+struct PostGeom {
+    int N, A, C, D, M;               // D = 5+C, M = rows per image
+    int h[2], w[2], hw[2];
+    float stride[2];
+    double anc[2][kMaxA][2];
+    const float* reg[2];
+    const float* obj[2];
+    const float* cls[2];
+};
+
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// (value, index) argmax, ties -> smaller index; every lane ends with the same pair
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// Stage the 5A+C logits of `ncell` consecutive cells of one level into S[ch][kSStride] (coalesced reads).
+__device__ __forceinline__ void stage_cells(float* __restrict__ S, const PostGeom& g, int n, int lv, int cell0, int ncell) {
+    const int A = g.A, C = g.C, hw = g.hw[lv];
+    const int nch = 5 * A + C;
+    for (int i = threadIdx.x; i < nch * kChunkCells; i += NT) {
+        const int ch = i >> 5, cl = i & 31;
+        if (cl < ncell) {
+            const float* src;
+            if (ch < 4 * A) src = g.reg[lv] + ((long long)n * 4 * A + ch) * hw;
+            else if (ch < 5 * A) src = g.obj[lv] + ((long long)n * A + (ch - 4 * A)) * hw;
+            else src = g.cls[lv] + ((long long)n * C + (ch - 5 * A)) * hw;
+            S[ch * kSStride + cl] = __ldg(src + cell0 + cl);
+        }
+    }
+}
+
+// One warp decodes one staged cell.  Lane l keeps softmax probabilities of classes l, l+32, ...;
+// lanes a < A additionally keep (cx, cy, w, h, obj) of anchor a.  utils/utils.py:331-343.
+struct CellRegs {
+    float p[kCPL];
+    float bx, by, bw, bh, ob;
+};
+__device__ __forceinline__ void decode_cell(const float* __restrict__ S, const PostGeom& g, int lv, int cell, int cl,
+                                            int lane, CellRegs& r) {
+    const int A = g.A, C = g.C;
+    float l[kCPL];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kCPL; ++j) {
+        const int c = lane + 32 * j;
+        l[j] = (c < C) ? S[(5 * A + c) * kSStride + cl] : -INFINITY;
+        m = fmaxf(m, l[j]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kCPL; ++j) {
+        const int c = lane + 32 * j;
+        l[j] = (c < C) ? expf(__fsub_rn(l[j], m)) : 0.f;
+        sum = __fadd_rn(sum, l[j]);
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < kCPL; ++j) r.p[j] = __fdiv_rn(l[j], sum);
+    r.bx = r.by = r.bw = r.bh = r.ob = 0.f;
+    if (lane < A) {
+        const int y = cell / g.w[lv], x = cell - y * g.w[lv];
+        const float* s = S + (4 * lane) * kSStride + cl;
+        const float sx = sigmoid_rn(s[0]), sy = sigmoid_rn(s[kSStride]);
+        const float sw = sigmoid_rn(s[2 * kSStride]), sh = sigmoid_rn(s[3 * kSStride]);
+        const float st = g.stride[lv];
+        r.bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), (float)x), st);
+        r.by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), (float)y), st);
+        const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+        // (s*2)**2 in fp32, then the float64 anchor promotes the product (utils/utils.py:305-306,337)
+        r.bw = (float)__dmul_rn((double)__fmul_rn(tw, tw), g.anc[lv][lane][0]);
+        r.bh = (float)__dmul_rn((double)__fmul_rn(th, th), g.anc[lv][lane][1]);
+        r.ob = sigmoid_rn(S[(4 * A + lane) * kSStride + cl]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode kernel: grid (chunks per image, N)
+__global__ void __launch_bounds__(NT)
+decode_kernel(PostGeom g, float* __restrict__ out, int chunks0) {
+    __shared__ float S[(5 * kMaxA + 32 * kCPL) * kSStride];
+    const int n = blockIdx.y;
+    const int lv = blockIdx.x < chunks0 ? 0 : 1;
+    const int cell0 = (lv ? blockIdx.x - chunks0 : blockIdx.x) * kChunkCells;
+    const int ncell = min(kChunkCells, g.hw[lv] - cell0);
+    stage_cells(S, g, n, lv, cell0, ncell);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = g.A, C = g.C, D = g.D;
+    const long long row_base = (long long)n * g.M + (lv ? (long long)g.hw[0] * A : 0);
+    for (int cl = warp; cl < ncell; cl += NT / 32) {
+        CellRegs r;
+        decode_cell(S, g, lv, cell0 + cl, cl, lane, r);
+        float* o = out + (row_base + (long long)(cell0 + cl) * A) * D;
+        if (lane < A) {
+            float* b = o + (long long)lane * D;
+            b[0] = r.bx; b[1] = r.by; b[2] = r.bw; b[3] = r.bh; b[4] = r.ob;
+        }
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int j = 0; j < kCPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < C) o[(long long)a * D + 5 + c] = r.p[j];       // same cls row for every anchor (:326)
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NMS
+struct NmsParams {
+    float conf_thres;
+    double iou_thres;
+    const int* class_filter;
+    int n_filter;
+    int max_det;
+    float max_wh;
+    float* out;        // [N,max_det,6]
+    int* counts;       // [N]
+    int* kept_idx;     // [N,max_det] or null
+    int M;             // candidate rows per image
+    int MCp;           // pow2 >= M
+};
+
+struct NmsSmem {
+    unsigned long long* keys;   // [MCp]
+    float4* cbox;               // [M]  xyxy, not offset
+    unsigned short* ccls;       // [M]
+    float4* kbox;               // [max_det] offset boxes of kept
+    float* karea;               // [max_det]
+    float4* chbox;              // [64]
+    float* charea;              // [64]
+    unsigned int* cmask;        // [64][2]
+    unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits
+};
+
+__host__ __device__ inline size_t nms_smem_bytes(int M, int MCp, int max_det) {
+    size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (((size_t)M * 2 + 15) & ~(size_t)15);
+    b += (size_t)max_det * 16 + (((size_t)max_det * 4 + 15) & ~(size_t)15);
+    b += kNmsChunk * 16 + kNmsChunk * 4 + kNmsChunk * 8 + 32;
+    return b;
+}
+
+__device__ __forceinline__ NmsSmem carve(unsigned char* base, int M, int MCp, int max_det) {
+    NmsSmem s;
+    s.keys = reinterpret_cast<unsigned long long*>(base); base += (size_t)MCp * 8;
+    s.cbox = reinterpret_cast<float4*>(base); base += (size_t)M * 16;
+    s.ccls = reinterpret_cast<unsigned short*>(base); base += (((size_t)M * 2 + 15) & ~(size_t)15);
+    s.kbox = reinterpret_cast<float4*>(base); base += (size_t)max_det * 16;
+    s.karea = reinterpret_cast<float*>(base); base += (((size_t)max_det * 4 + 15) & ~(size_t)15);
+    s.chbox = reinterpret_cast<float4*>(base); base += kNmsChunk * 16;
+    s.charea = reinterpret_cast<float*>(base); base += kNmsChunk * 4;
+    s.cmask = reinterpret_cast<unsigned int*>(base); base += kNmsChunk * 8;
+    s.misc = reinterpret_cast<unsigned int*>(base);
+    return s;
+}
+
+__device__ __forceinline__ unsigned int f2sortable(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sortable2f(unsigned int s) {
+    return __uint_as_float((s & 0x80000000u) ? (s & 0x7fffffffu) : ~s);
+}
+
+__device__ __forceinline__ bool class_ok(const NmsParams& p, int cls) {
+    if (!p.class_filter) return true;
+    bool ok = false;
+    for (int k = 0; k < p.n_filter; ++k) ok |= (p.class_filter[k] == cls);
+    return ok;
+}
+
+// xywh -> xyxy (utils/utils.py:67-74) and push; called by one lane.
+__device__ __forceinline__ void push_candidate(const NmsSmem& s, float cx, float cy, float w, float h, float conf, int cls,
+                                               int row) {
+    const unsigned int slot = atomicAdd(&s.misc[0], 1u);
+    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+    s.cbox[slot] = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    s.ccls[slot] = (unsigned short)cls;
+    s.keys[slot] = ((unsigned long long)f2sortable(conf) << 32) |
+                   ((unsigned long long)(0xFFFFu - (unsigned)row) << 16) | (unsigned long long)slot;
+}
+
+__device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& b, float ab, double thr) {
+    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+    return (double)ovr > thr;
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* keys, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += NT) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Sort the pushed candidates and run the blocked greedy suppression.  All threads of the CTA call this.
+__device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
+    __syncthreads();
+    const int cnt = (int)s.misc[0];
+    int n2 = 64;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = cnt + threadIdx.x; i < n2; i += NT) s.keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(s.keys, n2);
+
+    float* out = p.out + (long long)n * p.max_det * 6;
+    int* kidx = p.kept_idx ? p.kept_idx + (long long)n * p.max_det : nullptr;
+    int nk = 0;
+    const int t = threadIdx.x;
+    for (int c0 = 0; c0 < cnt && nk < p.max_det; c0 += kNmsChunk) {
+        const int cn = min(kNmsChunk, cnt - c0);
+        if (t < kNmsChunk) {
+            s.cmask[2 * t] = 0u; s.cmask[2 * t + 1] = 0u;
+            if (t < cn) {
+                const unsigned int slot = (unsigned int)(s.keys[c0 + t] & 0xFFFFull);
+                const float4 b = s.cbox[slot];
+                const float off = __fmul_rn((float)s.ccls[slot], p.max_wh);            // utils/utils.py:283
+                const float4 ob = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+                s.chbox[t] = ob;
+                s.charea[t] = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
+            }
+        }
+        if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }
+        __syncthreads();
+        {   // (a) chunk candidates against everything kept so far
+            const int j = t & (kNmsChunk - 1), q = t / kNmsChunk;
+            if (j < cn) {
+                const float4 bj = s.chbox[j];
+                const float aj = s.charea[j];
+                bool dead = false;
+                for (int i = q; i < nk && !dead; i += NT / kNmsChunk) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p.iou_thres);
+                if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
+            }
+        }
+        {   // (b) pairs inside the chunk: thread -> row i, 16 columns
+            const int i = t >> 2, jq = t & 3;
+            if (i < cn) {
+                const float4 bi = s.chbox[i];
+                const float ai = s.charea[i];
+                unsigned int bits = 0u;
+#pragma unroll 4
+                for (int e = 0; e < 16; ++e) {
+                    const int j = jq * 16 + e;
+                    if (j > i && j < cn && iou_gt(bi, ai, s.chbox[j], s.charea[j], p.iou_thres)) bits |= 1u << e;
+                }
+                if (bits) atomicOr(&s.cmask[2 * i + (jq >> 1)], bits << ((jq & 1) * 16));
+            }
+        }
+        __syncthreads();
+        if (t == 0) {   // (c) serial resolve
+            unsigned long long alive = ~(((unsigned long long)s.misc[2] << 32) | s.misc[1]);
+            if (cn < 64) alive &= (1ull << cn) - 1ull;
+            unsigned long long kept = 0ull;
+            int room = p.max_det - nk;
+            while (alive && room > 0) {
+                const int i = __ffsll((long long)alive) - 1;
+                kept |= 1ull << i;
+                --room;
+                const unsigned long long m = ((unsigned long long)s.cmask[2 * i + 1] << 32) | s.cmask[2 * i];
+                alive &= ~m;
+                alive &= ~(1ull << i);
+            }
+            s.misc[3] = (unsigned int)kept; s.misc[4] = (unsigned int)(kept >> 32);
+        }
+        __syncthreads();
+        const unsigned long long kept = ((unsigned long long)s.misc[4] << 32) | s.misc[3];
+        if (t < cn && ((kept >> t) & 1ull)) {   // (d) append
+            const int pos = nk + __popcll(kept & ((1ull << t) - 1ull));
+            s.kbox[pos] = s.chbox[t];
+            s.karea[pos] = s.charea[t];
+            const unsigned long long key = s.keys[c0 + t];
+            const unsigned int slot = (unsigned int)(key & 0xFFFFull);
+            const float4 b = s.cbox[slot];
+            float* o = out + pos * 6;
+            o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+            o[4] = sortable2f((unsigned int)(key >> 32));
+            o[5] = (float)s.ccls[slot];
+            if (kidx) kidx[pos] = 0xFFFF - (int)((key >> 16) & 0xFFFFull);
+        }
+        nk += __popcll(kept);
+        __syncthreads();
+    }
+    if (t == 0) p.counts[n] = nk;
+    for (int i = nk * 6 + t; i < p.max_det * 6; i += NT) out[i] = 0.f;
+    if (kidx) for (int i = nk + t; i < p.max_det; i += NT) kidx[i] = -1;
+}
+
+// NMS from an [N,M,5+C] tensor: one CTA per image, warp per row for the scoring pass.
+__global__ void __launch_bounds__(NT)
+nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
+    const int n = blockIdx.x;
+    if (threadIdx.x == 0) s.misc[0] = 0u;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = 5 + C;
+    const float* img = dets + (long long)n * p.M * D;
+    for (int r = warp; r < p.M; r += NT / 32) {
+        const float* row = img + (long long)r * D;
+        const float obj = __ldg(row + 4);
+        if (!(obj > p.conf_thres)) continue;                          // utils/utils.py:254 (warp uniform)
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = __fmul_rn(__ldg(row + 5 + c), obj);        // :261
+            if (v > best) { best = v; bi = c; }
+        }
+        warp_argmax(best, bi);                                        // :267 first max
+        if (lane == 0 && best > p.conf_thres && class_ok(p, bi))      // :268, :271-272
+            push_candidate(s, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r);
+    }
+    sort_and_suppress(s, p, n);
+}
+
+// Fused: candidates come straight from the head logits (same device code as decode_kernel).
+__global__ void __launch_bounds__(NT)
+decode_nms_kernel(PostGeom g, NmsParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
+    float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
+    const int n = blockIdx.x;
+    if (threadIdx.x == 0) s.misc[0] = 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = g.A, C = g.C;
+    for (int lv = 0; lv < 2; ++lv) {
+        const int row0 = lv ? g.hw[0] * A : 0;
+        for (int cell0 = 0; cell0 < g.hw[lv]; cell0 += kChunkCells) {
+            const int ncell = min(kChunkCells, g.hw[lv] - cell0);
+            __syncthreads();
+            stage_cells(S, g, n, lv, cell0, ncell);
+            __syncthreads();
+            for (int cl = warp; cl < ncell; cl += NT / 32) {
+                CellRegs r;
+                decode_cell(S, g, lv, cell0 + cl, cl, lane, r);
+                for (int a = 0; a < A; ++a) {
+                    const float obj = __shfl_sync(0xffffffffu, r.ob, a);
+                    if (!(obj > p.conf_thres)) continue;
+                    float best = -INFINITY;
+                    int bi = 0x7fffffff;
+#pragma unroll
+                    for (int j = 0; j < kCPL; ++j) {
+                        const int c = lane + 32 * j;
+                        if (c < C) {
+                            const float v = __fmul_rn(r.p[j], obj);
+                            if (v > best) { best = v; bi = c; }
+                        }
+                    }
+                    warp_argmax(best, bi);
+                    if (lane == a && best > p.conf_thres && class_ok(p, bi))
+                        push_candidate(s, r.bx, r.by, r.bw, r.bh, best, bi, row0 + (cell0 + cl) * A + a);
+                }
+            }
+        }
+    }
+    sort_and_suppress(s, p, n);
+}
+
+int fill_geom(PostGeom& g, const float* const preds[6], int N, int H, int W, int A, int C, const double* anchors_host) {
+    if (!preds || !anchors_host || N <= 0 || A <= 0 || A > kMaxA || C <= 0 || C > 32 * kCPL || H % 32 || W % 32 || H <= 0 || W <= 0) {
+        set_error("decode: bad arguments (N=%d H=%d W=%d A=%d C=%d; need A<=%d, C<=%d, H,W multiples of 32)", N, H, W, A, C,
+                  kMaxA, 32 * kCPL);
+        return YFV2_EINVAL;
+    }
+    g.N = N; g.A = A; g.C = C; g.D = 5 + C;
+    for (int lv = 0; lv < 2; ++lv) {
+        const int s = lv ? 32 : 16;
+        g.h[lv] = H / s; g.w[lv] = W / s; g.hw[lv] = g.h[lv] * g.w[lv];
+        g.stride[lv] = (float)((double)H / (double)g.h[lv]);      // cfg["height"] / h, one stride for both axes (:332)
+        for (int a = 0; a < A; ++a) {
+            g.anc[lv][a][0] = anchors_host[(lv * A + a) * 2];
+            g.anc[lv][a][1] = anchors_host[(lv * A + a) * 2 + 1];
+        }
+        g.reg[lv] = preds[3 * lv]; g.obj[lv] = preds[3 * lv + 1]; g.cls[lv] = preds[3 * lv + 2];
+        if (!g.reg[lv] || !g.obj[lv] || !g.cls[lv]) { set_error("decode: null head tensor"); return YFV2_EINVAL; }
+    }
+    g.M = (g.hw[0] + g.hw[1]) * A;
+    return YFV2_OK;
+}
+
+int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int* class_filter, int n_filter, int max_det,
+             float max_wh, float* out, int* counts, int* kept_idx) {
+    if (!out || !counts || max_det <= 0 || max_det > 4096 || M <= 0) { set_error("nms: bad arguments"); return YFV2_EINVAL; }
+    if (M > YFV2_NMS_MAX_CAND) { set_error("nms: M=%d candidates per image exceeds %d", M, YFV2_NMS_MAX_CAND); return YFV2_EUNSUPPORTED; }
+    p.conf_thres = conf_thres; p.iou_thres = iou_thres;
+    p.class_filter = n_filter > 0 ? class_filter : nullptr; p.n_filter = n_filter;
+    p.max_det = max_det; p.max_wh = max_wh; p.out = out; p.counts = counts; p.kept_idx = kept_idx; p.M = M;
+    p.MCp = 64;
+    while (p.MCp < M) p.MCp <<= 1;
+    return YFV2_OK;
+}
+}  // namespace
+}  // namespace yfv2
+
+using namespace yfv2;
+
+extern "C" int yfv2_decode(const float* const preds[6], int N, int H, int W, int A, int C, const double* anchors_host,
+                           float* out, void* stream) {
+    PostGeom g;
+    int rc = fill_geom(g, preds, N, H, W, A, C, anchors_host);
+    if (rc) return rc;
+    if (!out) { set_error("decode: null output"); return YFV2_EINVAL; }
+    const int chunks0 = (g.hw[0] + kChunkCells - 1) / kChunkCells, chunks1 = (g.hw[1] + kChunkCells - 1) / kChunkCells;
+    decode_kernel<<<dim3(chunks0 + chunks1, N), NT, 0, (cudaStream_t)stream>>>(g, out, chunks0);
+    YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_nms_workspace_bytes(int N, int M, int C, size_t* bytes) {
+    (void)N; (void)M; (void)C;
+    if (!bytes) return YFV2_EINVAL;
+    *bytes = 0;       // the blocked greedy pass keeps all of its state in shared memory
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_nms(const float* dets, int N, int M, int C, float conf_thres, double iou_thres, const int* class_filter,
+                        int n_filter, int max_det, float max_wh, float* out, int* counts, int* kept_idx, void* workspace,
+                        void* stream) {
+    (void)workspace;
+    if (!dets || N <= 0 || C <= 0) { set_error("nms: bad arguments"); return YFV2_EINVAL; }
+    NmsParams p;
+    int rc = fill_nms(p, M, conf_thres, iou_thres, class_filter, n_filter, max_det, max_wh, out, counts, kept_idx);
+    if (rc) return rc;
+    const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det);
+    if (bytes > kSmemCap) { set_error("nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
+    YFV2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    nms_kernel<<<N, NT, bytes, (cudaStream_t)stream>>>(dets, C, p);
+    YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W, int A, int C, const double* anchors_host,
+                               float conf_thres, double iou_thres, const int* class_filter, int n_filter, int max_det,
+                               float max_wh, float* out, int* counts, int* kept_idx, void* workspace, void* stream) {
+    (void)workspace;
+    PostGeom g;
+    int rc = fill_geom(g, preds, N, H, W, A, C, anchors_host);
+    if (rc) return rc;
+    NmsParams p;
+    rc = fill_nms(p, g.M, conf_thres, iou_thres, class_filter, n_filter, max_det, max_wh, out, counts, kept_idx);
+    if (rc) return rc;
+    const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (size_t)(5 * A + C) * kSStride * sizeof(float);
+    if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
+    YFV2_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    decode_nms_kernel<<<N, NT, bytes, (cudaStream_t)stream>>>(g, p);
+    YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}

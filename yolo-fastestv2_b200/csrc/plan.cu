@@ -1,0 +1,425 @@
+// Host side of libyfv2.so: plan construction (shape bookkeeping, channel-plane tables, packed-weight and
+// workspace layouts), weight packing, and the C ABI declared in include/yfv2.h.
+//
+// Mirrors the wiring of the reference model (model/detector.py:8-47, model/fpn.py:31-64,
+// model/backbone/shufflenetv2.py:65-109) without any of its module objects: the plan is a flat list of
+// fused-kernel launches over plane pools.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace yfv2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static thread_local int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+namespace {
+
+constexpr int kStageRepeats[3] = {4, 8, 4};          // shufflenetv2.py:69
+constexpr int kStageWidth[3] = {24, 48, 96};         // branch width = out_channels / 2 (detector.py:11)
+constexpr int kNumBlocks = 16;
+constexpr int kFpnDepth = 72;                        // detector.py:10
+
+// ---- pack kernels ---------------------------------------------------------------------------------------
+// w: [Nout][K] row-major conv weight.  Writes Wt[k][n_off+n], scale/shift[n_off+n] with row length Np.
+// BN folded as PyTorch's eval path does: alpha = invstd*gamma, beta' = beta - mean*alpha.
+__global__ void pack_pw_kernel(const float* __restrict__ w, int Nout, int K, const float* gamma, const float* beta,
+                               const float* mean, const float* var, const float* bias, float* Wt, int Np, int n_off,
+                               float* scale, float* shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Nout * K) {
+        const int n = i / K, k = i - n * K;
+        Wt[(size_t)k * Np + n_off + n] = w[i];
+    }
+    if (i < Nout) {
+        float sc = 1.0f, sh = 0.0f;
+        if (gamma) {
+            const float invstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[i], kBnEps)));
+            sc = __fmul_rn(invstd, gamma[i]);
+            sh = __fsub_rn(beta[i], __fmul_rn(mean[i], sc));
+        } else if (bias) {
+            sh = bias[i];
+        }
+        scale[n_off + i] = sc;
+        shift[n_off + i] = sh;
+    }
+}
+
+// w: [C][KK] depthwise weight -> per channel [KK taps][scale][shift][pad] with row length R
+__global__ void pack_dw_kernel(const float* __restrict__ w, int Cn, int KK, int R, const float* gamma, const float* beta,
+                               const float* mean, const float* var, float* dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Cn * KK) {
+        const int c = i / KK, t = i - c * KK;
+        dst[(size_t)c * R + t] = w[i];
+    }
+    if (i < Cn) {
+        const float invstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[i], kBnEps)));
+        const float sc = __fmul_rn(invstd, gamma[i]);
+        dst[(size_t)i * R + KK] = sc;
+        dst[(size_t)i * R + KK + 1] = __fsub_rn(beta[i], __fmul_rn(mean[i], sc));
+    }
+}
+
+struct Cursor {           // walks parameters / BN layers in state_dict order
+    const float* const* params;
+    const float* const* bn;
+    int p = 0, b = 0;
+};
+
+}  // namespace
+}  // namespace yfv2
+
+using namespace yfv2;
+
+struct yfv2_plan {
+    int device, N, H, W, A, C, training;
+    int h[4], w[4];                    // strides 4, 8, 16, 32
+    size_t plane[4];                   // plane stride (floats) per resolution
+    int pool_planes[4];                // 24, 72, 144, 288
+    size_t off_pool[4];
+    size_t off_s2, off_s3, off_t[4];   // t: cls2, reg2, cls3, reg3 mid-block scratch
+    size_t ws_floats;
+    size_t pk_stem, pk_block[kNumBlocks], pk_fpn3, pk_fpn2, pk_head[4], pk_out_reg, pk_out_oc, pk_floats;
+    int blk_K[kNumBlocks], blk_stride[kNumBlocks], blk_res[kNumBlocks];   // res = index of OUTPUT resolution
+    ChanTab tin[kNumBlocks], tout[kNumBlocks];
+    ChanTab c2, c3;
+    int launches;
+};
+
+namespace {
+
+Planes pool_planes(const yfv2_plan* p, float* ws, int r) {
+    Planes P;
+    P.base = ws + p->off_pool[r];
+    P.sC = (long long)p->plane[r];
+    P.sN = (long long)p->plane[r] * p->pool_planes[r];
+    P.H = p->h[r]; P.W = p->w[r];
+    return P;
+}
+Planes flat_planes(const yfv2_plan* p, float* ws, size_t off, int r) {
+    Planes P;
+    P.base = ws + off;
+    P.sC = (long long)p->plane[r];
+    P.sN = (long long)p->plane[r] * kFpnDepth;
+    P.H = p->h[r]; P.W = p->w[r];
+    return P;
+}
+
+void build_tables(yfv2_plan* p) {
+    std::vector<int> L(24);
+    for (int i = 0; i < 24; ++i) L[i] = i;
+    int bi = 0;
+    for (int st = 0; st < 3; ++st) {
+        const int K = kStageWidth[st];
+        std::vector<int> freep;
+        for (int rep = 0; rep < kStageRepeats[st]; ++rep, ++bi) {
+            p->blk_K[bi] = K;
+            p->blk_res[bi] = st + 1;
+            if (rep == 0) {
+                // stride 2: read every logical channel of the previous stage, write 2K fresh planes 0..2K-1
+                p->blk_stride[bi] = 2;
+                for (int i = 0; i < K; ++i) p->tin[bi].c[i] = (unsigned short)L[i];
+                L.resize(2 * K);
+                for (int i = 0; i < 2 * K; ++i) { L[i] = i; p->tout[bi].c[i] = (unsigned short)i; }
+                freep.clear();
+                for (int i = 2 * K; i < 3 * K; ++i) freep.push_back(i);
+            } else {
+                // stride 1: channel_shuffle (shufflenetv2.py:57-63): even logical channels pass through,
+                // odd ones feed branch_main; output = cat(pass, main)
+                p->blk_stride[bi] = 1;
+                std::vector<int> pass, mainin;
+                for (int i = 0; i < 2 * K; ++i) (i % 2 ? mainin : pass).push_back(L[i]);
+                for (int i = 0; i < K; ++i) {
+                    p->tin[bi].c[i] = (unsigned short)mainin[i];
+                    p->tout[bi].c[i] = (unsigned short)freep[i];
+                }
+                L = pass;
+                L.insert(L.end(), freep.begin(), freep.end());
+                freep = mainin;
+            }
+        }
+        if (st == 1) for (int i = 0; i < 96; ++i) p->c2.c[i] = (unsigned short)L[i];
+        if (st == 2) for (int i = 0; i < 192; ++i) p->c3.c[i] = (unsigned short)L[i];
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" int yfv2_abi_version(void) { return YFV2_ABI_VERSION; }
+extern "C" const char* yfv2_last_error(void) { return g_err; }
+
+extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W, int A, int C, int training) {
+    if (!out || N <= 0 || H <= 0 || W <= 0 || H % 32 || W % 32 || A <= 0 || A > 8 || C <= 0 || C > 256) {
+        set_error("plan_create: bad arguments (N=%d H=%d W=%d A=%d C=%d); H and W must be multiples of 32, A<=8, C<=256",
+                  N, H, W, A, C);
+        return YFV2_EINVAL;
+    }
+    if (training) {
+        set_error("plan_create: training plans (batch-statistics BN + backward) are not implemented in this build");
+        return YFV2_EUNSUPPORTED;
+    }
+    yfv2_plan* p = new (std::nothrow) yfv2_plan();
+    if (!p) { set_error("plan_create: out of host memory"); return YFV2_ENOMEM; }
+    memset(p, 0, sizeof(*p));
+    p->device = device; p->N = N; p->H = H; p->W = W; p->A = A; p->C = C; p->training = training;
+    const int pools[4] = {24, 72, 144, 288};
+    size_t off = 0;
+    for (int r = 0; r < 4; ++r) {
+        p->h[r] = H >> (r + 2); p->w[r] = W >> (r + 2);
+        p->plane[r] = align_up((size_t)p->h[r] * p->w[r], 4);
+        p->pool_planes[r] = pools[r];
+        p->off_pool[r] = off;
+        off += align_up(p->plane[r] * pools[r] * (size_t)N, 64);
+    }
+    p->off_s2 = off; off += align_up(p->plane[2] * kFpnDepth * (size_t)N, 64);
+    p->off_s3 = off; off += align_up(p->plane[3] * kFpnDepth * (size_t)N, 64);
+    for (int i = 0; i < 4; ++i) {
+        p->off_t[i] = off;
+        off += align_up(p->plane[i < 2 ? 2 : 3] * kFpnDepth * (size_t)N, 64);
+    }
+    p->ws_floats = off;
+    build_tables(p);
+    size_t pk = 0;
+    p->pk_stem = pk; pk += align_up(kStemPackFloats, 4);
+    for (int b = 0; b < kNumBlocks; ++b) { p->pk_block[b] = pk; pk += align_up(shuffle_pack_floats(p->blk_K[b], p->blk_stride[b]), 4); }
+    p->pk_fpn3 = pk; pk += pw_pack_floats(192, kFpnDepth);
+    p->pk_fpn2 = pk; pk += pw_pack_floats(288, kFpnDepth);
+    for (int i = 0; i < 4; ++i) { p->pk_head[i] = pk; pk += align_up(head_pack_floats(), 4); }
+    p->pk_out_reg = pk; pk += pw_pack_floats(kFpnDepth, 4 * A);
+    p->pk_out_oc = pk; pk += pw_pack_floats(kFpnDepth, A + C);
+    p->pk_floats = pk;
+    p->launches = 1 + kNumBlocks + 2 + 4;
+    *out = p;
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_plan_destroy(yfv2_plan* p) {
+    delete p;
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_plan_workspace_bytes(const yfv2_plan* p, size_t* bytes) {
+    if (!p || !bytes) { set_error("workspace_bytes: null argument"); return YFV2_EINVAL; }
+    *bytes = p->ws_floats * sizeof(float);
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_plan_packed_bytes(const yfv2_plan* p, size_t* bytes) {
+    if (!p || !bytes) { set_error("packed_bytes: null argument"); return YFV2_EINVAL; }
+    *bytes = p->pk_floats * sizeof(float);
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_plan_forward_launches(const yfv2_plan* p, int* n) {
+    if (!p || !n) { set_error("forward_launches: null argument"); return YFV2_EINVAL; }
+    *n = p->launches;
+    return YFV2_OK;
+}
+
+namespace {
+
+int pack_pw(Cursor& cur, bool bn, bool bias, int Nout, int K, float* pack, int Np, int n_off, cudaStream_t s) {
+    const float* w = cur.params[cur.p];
+    const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr, *bi = nullptr;
+    if (bn) { g = cur.params[cur.p + 1]; b = cur.params[cur.p + 2]; m = cur.bn[2 * cur.b]; v = cur.bn[2 * cur.b + 1]; cur.p += 3; cur.b += 1; }
+    else if (bias) { bi = cur.params[cur.p + 1]; cur.p += 2; }
+    else cur.p += 1;
+    if (!w || (bn && (!g || !b || !m || !v)) || (bias && !bi)) { set_error("pack_weights: null tensor pointer near param %d", cur.p); return YFV2_EINVAL; }
+    const int total = Nout * K;
+    pack_pw_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, Nout, K, g, b, m, v, bi, pack, Np, n_off, pack + (size_t)K * Np,
+                                                        pack + (size_t)K * Np + Np);
+    YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}
+
+int pack_dw(Cursor& cur, int Cn, int ksz, float* pack, cudaStream_t s) {
+    const float* w = cur.params[cur.p];
+    const float *g = cur.params[cur.p + 1], *b = cur.params[cur.p + 2], *m = cur.bn[2 * cur.b], *v = cur.bn[2 * cur.b + 1];
+    cur.p += 3; cur.b += 1;
+    if (!w || !g || !b || !m || !v) { set_error("pack_weights: null tensor pointer near param %d", cur.p); return YFV2_EINVAL; }
+    const int KK = ksz * ksz, R = ksz == 3 ? 12 : 28;
+    pack_dw_kernel<<<(Cn * KK + 255) / 256, 256, 0, s>>>(w, Cn, KK, R, g, b, m, v, pack);
+    YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+}  // namespace
+
+extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const float* const* bn_running, void* packed,
+                                 void* stream) {
+    if (!p || !params || !bn_running || !packed) { set_error("pack_weights: null argument"); return YFV2_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    float* pk = (float*)packed;
+    YFV2_CUDA(cudaMemsetAsync(pk, 0, p->pk_floats * sizeof(float), s));
+    Cursor cur{params, bn_running};
+    // backbone.first_conv (shufflenetv2.py:74-78)
+    TRY(pack_pw(cur, true, false, 24, 27, pk + p->pk_stem, 24, 0, s));
+    for (int b = 0; b < kNumBlocks; ++b) {
+        const int K = p->blk_K[b];
+        float* d = pk + p->pk_block[b];
+        const int pwn = pw_pack_floats(K, K), dwn = dw3_pack_floats(K);
+        if (p->blk_stride[b] == 2) {
+            // state_dict order: branch_main (pw1, dw, pw2) then branch_proj (dw, pw); pack order DWp|PWp|PW1|DW|PW2
+            TRY(pack_pw(cur, true, false, K, K, d + dwn + pwn, K, 0, s));
+            TRY(pack_dw(cur, K, 3, d + dwn + 2 * pwn, s));
+            TRY(pack_pw(cur, true, false, K, K, d + 2 * dwn + 2 * pwn, K, 0, s));
+            TRY(pack_dw(cur, K, 3, d, s));
+            TRY(pack_pw(cur, true, false, K, K, d + dwn, K, 0, s));
+        } else {
+            TRY(pack_pw(cur, true, false, K, K, d, K, 0, s));
+            TRY(pack_dw(cur, K, 3, d + pwn, s));
+            TRY(pack_pw(cur, true, false, K, K, d + pwn + dwn, K, 0, s));
+        }
+    }
+    // fpn: conv1x1_2, conv1x1_3, cls_head_2, reg_head_2, reg_head_3, cls_head_3 (fpn.py:35-49 registration order)
+    TRY(pack_pw(cur, true, false, kFpnDepth, 288, pk + p->pk_fpn2, kFpnDepth, 0, s));
+    TRY(pack_pw(cur, true, false, kFpnDepth, 192, pk + p->pk_fpn3, kFpnDepth, 0, s));
+    const int head_order[4] = {0, 1, 3, 2};     // pk_head index: 0 cls2, 1 reg2, 2 cls3, 3 reg3
+    for (int i = 0; i < 4; ++i) {
+        float* d = pk + p->pk_head[head_order[i]];
+        const int dwn = dw5_pack_floats(kFpnDepth), pwn = pw_pack_floats(kFpnDepth, kFpnDepth);
+        TRY(pack_dw(cur, kFpnDepth, 5, d, s));
+        TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + dwn, kFpnDepth, 0, s));
+        TRY(pack_dw(cur, kFpnDepth, 5, d + dwn + pwn, s));
+        TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + 2 * dwn + pwn, kFpnDepth, 0, s));
+    }
+    // output_reg_layers, output_obj_layers, output_cls_layers (detector.py:17-19); obj and cls share one pack
+    TRY(pack_pw(cur, false, true, 4 * p->A, kFpnDepth, pk + p->pk_out_reg, round4(4 * p->A), 0, s));
+    const int Moc = round4(p->A + p->C);
+    TRY(pack_pw(cur, false, true, p->A, kFpnDepth, pk + p->pk_out_oc, Moc, 0, s));
+    TRY(pack_pw(cur, false, true, p->C, kFpnDepth, pk + p->pk_out_oc, Moc, p->A, s));
+    if (cur.p != YFV2_NUM_PARAMS || cur.b != YFV2_NUM_BN) {
+        set_error("pack_weights: internal walk consumed %d params / %d BN layers", cur.p, cur.b);
+        return YFV2_EINVAL;
+    }
+    return YFV2_OK;
+}
+
+namespace {
+int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, float* const preds[6], void* workspace,
+                 cudaStream_t s) {
+    if (!p || !x || !packed || !preds || !workspace) { set_error("forward: null argument"); return YFV2_EINVAL; }
+    for (int i = 0; i < 6; ++i) if (!preds[i]) { set_error("forward: null output %d", i); return YFV2_EINVAL; }
+    float* ws = (float*)workspace;
+    const float* pk = (const float*)packed;
+
+    StemArgs st{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
+    TRY(launch_stem(st, s));
+    for (int b = 0; b < kNumBlocks; ++b) {
+        ShuffleArgs a;
+        a.K = p->blk_K[b]; a.stride = p->blk_stride[b]; a.N = p->N;
+        a.out = pool_planes(p, ws, p->blk_res[b]);
+        a.in = a.stride == 2 ? pool_planes(p, ws, p->blk_res[b] - 1) : a.out;
+        a.tin = p->tin[b]; a.tout = p->tout[b];
+        a.wpack = pk + p->pk_block[b];
+        TRY(launch_shuffle(a, s));
+    }
+    FpnArgs f;
+    f.N = p->N;
+    f.c3 = pool_planes(p, ws, 3); f.t3 = p->c3;
+    f.c2 = pool_planes(p, ws, 2); f.t2 = p->c2;
+    f.s3 = flat_planes(p, ws, p->off_s3, 3);
+    f.s2 = flat_planes(p, ws, p->off_s2, 2);
+    f.w3 = pk + p->pk_fpn3; f.w2 = pk + p->pk_fpn2;
+    TRY(launch_fpn(f, s));
+    for (int lv = 0; lv < 2; ++lv) {
+        HeadArgs h;
+        h.N = p->N; h.A = p->A; h.C = p->C;
+        h.s = lv ? f.s3 : f.s2;
+        h.t_cls = flat_planes(p, ws, p->off_t[2 * lv], 2 + lv);
+        h.t_reg = flat_planes(p, ws, p->off_t[2 * lv + 1], 2 + lv);
+        h.w_cls = pk + p->pk_head[2 * lv];
+        h.w_reg = pk + p->pk_head[2 * lv + 1];
+        h.w_out_reg = pk + p->pk_out_reg;
+        h.w_out_oc = pk + p->pk_out_oc;
+        h.reg = preds[3 * lv]; h.obj = preds[3 * lv + 1]; h.cls = preds[3 * lv + 2];
+        TRY(launch_heads(h, s));
+    }
+    return YFV2_OK;
+}
+}  // namespace
+
+extern "C" int yfv2_forward(yfv2_plan* p, const float* x, const void* packed, float* const preds[6], void* workspace,
+                            void* stream) {
+    return forward_impl(p, x, 0, packed, preds, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int yfv2_forward_u8(yfv2_plan* p, const uint8_t* x, const void* packed, float* const preds[6], void* workspace,
+                               void* stream) {
+    return forward_impl(p, x, 1, packed, preds, workspace, (cudaStream_t)stream);
+}
+
+// ---- whole step with host buffers ---------------------------------------------------------------------------
+namespace {
+struct DetectLayout {
+    size_t off_x, off_pred[6], off_out, off_counts, total;
+};
+DetectLayout detect_layout(const yfv2_plan* p, int max_det) {
+    DetectLayout L;
+    size_t off = align_up(p->ws_floats * sizeof(float), 256);
+    L.off_x = off; off += align_up((size_t)p->N * 3 * p->H * p->W, 256);
+    for (int lv = 0; lv < 2; ++lv) {
+        const size_t hw = (size_t)p->h[2 + lv] * p->w[2 + lv];
+        const int ch[3] = {4 * p->A, p->A, p->C};
+        for (int k = 0; k < 3; ++k) { L.off_pred[3 * lv + k] = off; off += align_up((size_t)p->N * ch[k] * hw * sizeof(float), 256); }
+    }
+    L.off_out = off; off += align_up((size_t)p->N * max_det * 6 * sizeof(float), 256);
+    L.off_counts = off; off += align_up((size_t)p->N * sizeof(int), 256);
+    L.total = off;
+    return L;
+}
+}  // namespace
+
+extern "C" size_t yfv2_detect_workspace_bytes(const yfv2_plan* p, int max_det) {
+    if (!p || max_det <= 0) return 0;
+    return detect_layout(p, max_det).total;
+}
+
+extern "C" int yfv2_detect_u8_host(yfv2_plan* p, const uint8_t* x_host, const void* packed, const double* anchors_host,
+                                   float conf_thres, double iou_thres, int max_det, float* out_host, int* counts_host,
+                                   void* workspace, void* stream) {
+    if (!p || !x_host || !packed || !anchors_host || !out_host || !counts_host || !workspace || max_det <= 0) {
+        set_error("detect_u8_host: null argument");
+        return YFV2_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const DetectLayout L = detect_layout(p, max_det);
+    unsigned char* ws = (unsigned char*)workspace;
+    uint8_t* x_dev = ws + L.off_x;
+    float* preds[6];
+    for (int i = 0; i < 6; ++i) preds[i] = (float*)(ws + L.off_pred[i]);
+    float* out_dev = (float*)(ws + L.off_out);
+    int* counts_dev = (int*)(ws + L.off_counts);
+    YFV2_CUDA(cudaMemcpyAsync(x_dev, x_host, (size_t)p->N * 3 * p->H * p->W, cudaMemcpyHostToDevice, s));
+    TRY(forward_impl(p, x_dev, 1, packed, preds, ws, s));
+    TRY(yfv2_decode_nms(preds, p->N, p->H, p->W, p->A, p->C, anchors_host, conf_thres, iou_thres, nullptr, 0, max_det,
+                        4096.0f, out_dev, counts_dev, nullptr, nullptr, stream));
+    YFV2_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)p->N * max_det * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    YFV2_CUDA(cudaMemcpyAsync(counts_host, counts_dev, (size_t)p->N * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return YFV2_OK;
+}

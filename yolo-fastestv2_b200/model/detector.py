@@ -1,0 +1,74 @@
+"""Drop-in replacement for the reference's model/detector.py:Detector.
+
+Same constructor and forward signature, same sub-module tree (hence the same 444 state_dict keys, so
+modelzoo checkpoints load with strict=True), but forward() runs the fused CUDA kernels of libyfv2.so
+through the C ABI (include/yfv2.h).  CUDA only: a CPU tensor raises — there is no fallback path.
+"""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+import yfv2_engine                                           # noqa: E402
+from model.fpn import LightFPN                               # noqa: E402
+from model.backbone.shufflenetv2 import ShuffleNetV2         # noqa: E402
+
+
+class Detector(nn.Module):
+    def __init__(self, classes, anchor_num, load_param, export_onnx=False):
+        super().__init__()
+        out_depth = 72
+        stage_out_channels = [-1, 24, 48, 96, 192]
+        self.export_onnx = export_onnx
+        self.classes, self.anchor_num = classes, anchor_num
+        self.backbone = ShuffleNetV2(stage_out_channels, load_param)
+        self.fpn = LightFPN(stage_out_channels[-2] + stage_out_channels[-1], stage_out_channels[-1], out_depth)
+        self.output_reg_layers = nn.Conv2d(out_depth, 4 * anchor_num, 1, 1, 0, bias=True)
+        self.output_obj_layers = nn.Conv2d(out_depth, anchor_num, 1, 1, 0, bias=True)
+        self.output_cls_layers = nn.Conv2d(out_depth, classes, 1, 1, 0, bias=True)
+        self._plans = {}
+
+    # ---- weight bookkeeping ---------------------------------------------------------------------------
+    def _weight_tensors(self):
+        params = list(self.parameters())
+        bn = []
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                bn += [m.running_mean, m.running_var]
+        return params, bn
+
+    def _plan_for(self, x):
+        N, _, H, W = x.shape
+        key = (x.device.index, N, H, W)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 8:
+                self._plans.pop(next(iter(self._plans)))
+            plan = yfv2_engine.Plan(x.device, N, H, W, self.anchor_num, self.classes, training=False)
+            self._plans[key] = plan
+        params, bn = self._weight_tensors()
+        version = tuple(t._version for t in params + bn) + tuple(t.data_ptr() for t in params[:1])
+        if plan.packed_version != version:
+            plan.pack(params, bn)
+            plan.packed_version = version
+        return plan
+
+    # ---- forward -----------------------------------------------------------------------------------------
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("yfv2 Detector runs on CUDA only (no CPU fallback); move the model and input to a GPU")
+        if self.training:
+            raise NotImplementedError("train-mode forward/backward kernels are not part of this build yet; call .eval()")
+        if self.export_onnx:
+            raise NotImplementedError("export_onnx=True head (sigmoid/softmax + NHWC concat) is not part of this build yet")
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input [N,3,H,W]")
+        plan = self._plan_for(x)
+        if x.dtype not in (torch.float32, torch.uint8):
+            x = x.float()
+        return plan.forward(x)

@@ -1,0 +1,72 @@
+"""Drop-in replacement for the hot-path functions of the reference's utils/utils.py:
+load_datafile (:13-65), handel_preds (:303-358), non_max_suppression (:232-296).
+
+handel_preds / non_max_suppression keep the reference's return types (a CPU [N,M,5+C] tensor; a list
+of CPU [n_i,6] tensors) but do all arithmetic in libyfv2.so kernels; one device->host copy per batch
+replaces the reference's per-image Python loops.  detect() is the fused fast path.
+"""
+import os
+import sys
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
+
+import yfv2_engine  # noqa: E402
+
+_LIST_KEYS = ("anchors", "steps")
+_STR_KEYS = ("model_name", "val", "train", "names", "pre_weights")
+_INT_KEYS = ("epochs", "batch_size", "classes", "width", "height", "anchor_num", "subdivisions")
+_FLOAT_KEYS = ("learning_rate",)
+
+
+def load_datafile(data_path):
+    """Parses the reference's `.data` format: `key=value` lines, blank lines and `[section]` lines skipped,
+    values typed by key (reference utils/utils.py:38-42); unknown keys are reported and ignored."""
+    assert os.path.exists(data_path), "data file not found: %s" % data_path
+    cfg = {k: None for k in ("model_name", "epochs", "steps", "batch_size", "subdivisions", "learning_rate", "pre_weights",
+                             "classes", "width", "height", "anchor_num", "anchors", "val", "train", "names")}
+    with open(data_path, "r") as f:
+        for line in f.readlines():
+            if line == "\n" or line[0] == "[":
+                continue
+            data = line.strip().split("=")
+            key = data[0]
+            if key not in cfg:
+                print("%s: unknown configuration item %s" % (data_path, data))
+            elif key in _INT_KEYS:
+                cfg[key] = int(data[1])
+            elif key in _STR_KEYS:
+                cfg[key] = data[1]
+            elif key in _FLOAT_KEYS:
+                cfg[key] = float(data[1])
+            elif key in _LIST_KEYS:
+                cfg[key] = [float(x) for x in data[1].split(",")]
+    return cfg
+
+
+def handel_preds(preds, cfg, device):
+    """[N, sum(h*w*A), 5+C] fp32 CPU tensor, as the reference returns (utils/utils.py:328,350-358)."""
+    return yfv2_engine.decode(preds, cfg).cpu()
+
+
+def _to_list(out, counts):
+    out, counts = out.cpu(), counts.cpu().tolist()
+    return [out[i, :c].clone() for i, c in enumerate(counts)]
+
+
+def non_max_suppression(prediction, conf_thres=0.3, iou_thres=0.45, classes=None):
+    """list (len N) of CPU fp32 [n_i,6] tensors (x1,y1,x2,y2,conf,cls), descending conf, at most 300 each."""
+    dev = prediction.device if prediction.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    if not torch.cuda.is_available():
+        raise RuntimeError("yfv2 non_max_suppression needs a CUDA device (no CPU fallback)")
+    out, counts, _ = yfv2_engine.nms(prediction.to(dev), conf_thres, iou_thres, classes, want_idx=False)
+    return _to_list(out, counts)
+
+
+def detect(preds, cfg, conf_thres=0.3, iou_thres=0.45, classes=None):
+    """Fused handel_preds + non_max_suppression: same list-of-[n_i,6] result without the candidate tensor."""
+    out, counts, _ = yfv2_engine.decode_nms(preds, cfg, conf_thres, iou_thres, classes)
+    return _to_list(out, counts)

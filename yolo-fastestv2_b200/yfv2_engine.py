@@ -1,0 +1,247 @@
+"""ctypes binding of libyfv2.so (include/yfv2.h) plus the small amount of host bookkeeping the Python
+mirror modules share: plan cache, weight packing, output allocation.  PyTorch is used for device
+memory and streams only; every device computation is a kernel inside libyfv2.so.
+
+There is NO CPU fallback: if the library is missing or the tensors are not on a CUDA device the calls
+raise.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libyfv2.so")
+_lib = None
+_lock = threading.Lock()
+
+MAX_DET = 300          # reference utils/utils.py:242
+MAX_WH = 4096.0        # reference utils/utils.py:241
+
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+# name -> (restype, argtypes); must list every prototype of include/yfv2.h (tests check this)
+PROTOTYPES = {
+    "yfv2_abi_version": (ctypes.c_int, []),
+    "yfv2_last_error": (ctypes.c_char_p, []),
+    "yfv2_plan_create": (ctypes.c_int, [_c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "yfv2_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "yfv2_plan_workspace_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "yfv2_plan_packed_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "yfv2_plan_forward_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "yfv2_pack_weights": (ctypes.c_int, [ctypes.c_void_p, _c_void_pp, _c_void_pp, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_void_pp, ctypes.c_void_p,
+                                    ctypes.c_void_p]),
+    "yfv2_forward_u8": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, _c_void_pp, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
+    "yfv2_decode": (ctypes.c_int, [_c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_nms_workspace_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "yfv2_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_double,
+                                ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_decode_nms": (ctypes.c_int, [_c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_detect_u8_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_detect_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
+}
+
+
+def lib():
+    """Loads libyfv2.so (once).  Raises if it has not been built — there is no fallback path."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_LIB_PATH):
+                    raise RuntimeError("libyfv2.so is missing (%s): build it with "
+                                       "`python yolo-fastestv2_b200/build.py` or __graft_entry__.build()" % _LIB_PATH)
+                L = ctypes.CDLL(_LIB_PATH)
+                for name, (res, args) in PROTOTYPES.items():
+                    fn = getattr(L, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = L
+    return _lib
+
+
+class Yfv2Error(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise Yfv2Error("%s failed (%d): %s" % (what, rc, lib().yfv2_last_error().decode("utf-8", "replace")))
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise Yfv2Error("%s must be a CUDA tensor: this implementation has no CPU path" % name)
+
+
+def anchors_array(cfg):
+    a = [float(v) for v in cfg["anchors"]]
+    return (ctypes.c_double * len(a))(*a)
+
+
+class Plan:
+    """One yfv2_plan with its workspace and packed-weight buffer (owned here as torch tensors)."""
+
+    def __init__(self, device, N, H, W, A, C, training=False, detect_max_det=0):
+        L = lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise Yfv2Error("plans exist on CUDA devices only")
+        self.N, self.H, self.W, self.A, self.C = N, H, W, A, C
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(L.yfv2_plan_create(ctypes.byref(self._h), self.device.index or 0, N, H, W, A, C, int(training)), "plan_create")
+        nb = ctypes.c_size_t()
+        _check(L.yfv2_plan_workspace_bytes(self._h, ctypes.byref(nb)), "workspace_bytes")
+        ws_bytes = nb.value
+        if detect_max_det:
+            ws_bytes = max(ws_bytes, L.yfv2_detect_workspace_bytes(self._h, detect_max_det))
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _check(L.yfv2_plan_packed_bytes(self._h, ctypes.byref(nb)), "packed_bytes")
+        self.packed = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        n = ctypes.c_int()
+        _check(L.yfv2_plan_forward_launches(self._h, ctypes.byref(n)), "forward_launches")
+        self.forward_launches = n.value
+        self.packed_version = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                lib().yfv2_plan_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    def pack(self, params, bn_running):
+        """params: 225 fp32 CUDA tensors in Detector.parameters() order; bn_running: 146 (mean, var, ...)."""
+        if len(params) != 225 or len(bn_running) != 146:
+            raise Yfv2Error("pack: expected 225 parameters and 146 BN buffers, got %d / %d" % (len(params), len(bn_running)))
+        keep = []
+        for t in list(params) + list(bn_running):
+            _require_cuda(t, "weight")
+            if t.dtype != torch.float32:
+                raise Yfv2Error("weights must be float32")
+            keep.append(t.detach().contiguous())
+        with torch.cuda.device(self.device):
+            _check(lib().yfv2_pack_weights(self._h, _ptr_array(keep[:225]), _ptr_array(keep[225:]),
+                                           ctypes.c_void_p(self.packed.data_ptr()), _stream(self.device)), "pack_weights")
+        return keep   # caller may drop it after the stream has run; kept alive by stream ordering of the allocator
+
+    def alloc_preds(self):
+        N, A, C = self.N, self.A, self.C
+        out = []
+        for s in (16, 32):
+            h, w = self.H // s, self.W // s
+            for ch in (4 * A, A, C):
+                out.append(torch.empty((N, ch, h, w), dtype=torch.float32, device=self.device))
+        return tuple(out)
+
+    def forward(self, x, preds=None):
+        _require_cuda(x, "x")
+        if tuple(x.shape) != (self.N, 3, self.H, self.W):
+            raise Yfv2Error("forward: input shape %s does not match the plan (%d,3,%d,%d)" % (tuple(x.shape), self.N, self.H, self.W))
+        if x.dtype not in (torch.float32, torch.uint8):
+            raise Yfv2Error("forward: input must be float32 or uint8")
+        x = x.contiguous()
+        if preds is None:
+            preds = self.alloc_preds()
+        fn = lib().yfv2_forward if x.dtype == torch.float32 else lib().yfv2_forward_u8
+        with torch.cuda.device(self.device):
+            _check(fn(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(self.packed.data_ptr()), _ptr_array(preds),
+                      ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)), "forward")
+        return preds
+
+    def detect_u8_host(self, x_host, anchors, conf_thres, iou_thres, out_host, counts_host, max_det=MAX_DET):
+        """Whole step from pinned host uint8 images to pinned host detections (asynchronous)."""
+        with torch.cuda.device(self.device):
+            _check(lib().yfv2_detect_u8_host(self._h, ctypes.c_void_p(x_host.data_ptr()), ctypes.c_void_p(self.packed.data_ptr()),
+                                             anchors, ctypes.c_float(conf_thres), ctypes.c_double(iou_thres), max_det,
+                                             ctypes.c_void_p(out_host.data_ptr()), ctypes.c_void_p(counts_host.data_ptr()),
+                                             ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)), "detect_u8_host")
+
+
+def decode(preds, cfg):
+    """handel_preds on the device: returns [N, M, 5+C] fp32 CUDA tensor."""
+    for p in preds:
+        _require_cuda(p, "preds")
+    preds = [p.detach().contiguous().float() for p in preds]
+    N, A4, h, w = preds[0].shape
+    A, C = preds[1].shape[1], preds[2].shape[1]
+    if len(preds) != 6 or A4 != 4 * A:
+        raise Yfv2Error("decode: expected the 6-tuple (reg,obj,cls) x 2 levels")
+    H, W = h * 16, w * 16
+    if cfg is not None and (int(cfg["height"]) != H or int(cfg["width"]) != W):
+        raise Yfv2Error("decode: head tensors are %dx%d/16 but cfg says %sx%s" % (H, W, cfg["height"], cfg["width"]))
+    M = (h * w + preds[3].shape[2] * preds[3].shape[3]) * A
+    out = torch.empty((N, M, 5 + C), dtype=torch.float32, device=preds[0].device)
+    with torch.cuda.device(out.device):
+        _check(lib().yfv2_decode(_ptr_array(preds), N, H, W, A, C, anchors_array(cfg), ctypes.c_void_p(out.data_ptr()),
+                                 _stream(out.device)), "decode")
+    return out
+
+
+def _filter_tensor(classes, device):
+    if classes is None:
+        return None, 0
+    t = torch.as_tensor(list(classes), dtype=torch.int32, device=device)
+    return t, t.numel()
+
+
+def nms(dets, conf_thres=0.3, iou_thres=0.45, classes=None, max_det=MAX_DET, want_idx=True):
+    """Device NMS.  Returns (out [N,max_det,6], counts [N] int32, kept_idx [N,max_det] int32 or None)."""
+    _require_cuda(dets, "dets")
+    dets = dets.detach().contiguous().float()
+    N, M, D = dets.shape
+    out = torch.empty((N, max_det, 6), dtype=torch.float32, device=dets.device)
+    counts = torch.empty((N,), dtype=torch.int32, device=dets.device)
+    idx = torch.empty((N, max_det), dtype=torch.int32, device=dets.device) if want_idx else None
+    filt, nf = _filter_tensor(classes, dets.device)
+    with torch.cuda.device(dets.device):
+        _check(lib().yfv2_nms(ctypes.c_void_p(dets.data_ptr()), N, M, D - 5, ctypes.c_float(conf_thres), ctypes.c_double(iou_thres),
+                              ctypes.c_void_p(filt.data_ptr()) if nf else None, nf, max_det, ctypes.c_float(MAX_WH),
+                              ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(counts.data_ptr()),
+                              ctypes.c_void_p(idx.data_ptr()) if want_idx else None, None, _stream(dets.device)), "nms")
+    return out, counts, idx
+
+
+def decode_nms(preds, cfg, conf_thres=0.3, iou_thres=0.45, classes=None, max_det=MAX_DET, want_idx=False):
+    """Fused handel_preds + non_max_suppression on the device (no [N,M,5+C] tensor)."""
+    for p in preds:
+        _require_cuda(p, "preds")
+    preds = [p.detach().contiguous().float() for p in preds]
+    N, _, h, w = preds[0].shape
+    A, C = preds[1].shape[1], preds[2].shape[1]
+    H, W = h * 16, w * 16
+    dev = preds[0].device
+    out = torch.empty((N, max_det, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((N,), dtype=torch.int32, device=dev)
+    idx = torch.empty((N, max_det), dtype=torch.int32, device=dev) if want_idx else None
+    filt, nf = _filter_tensor(classes, dev)
+    with torch.cuda.device(dev):
+        _check(lib().yfv2_decode_nms(_ptr_array(preds), N, H, W, A, C, anchors_array(cfg), ctypes.c_float(conf_thres),
+                                     ctypes.c_double(iou_thres), ctypes.c_void_p(filt.data_ptr()) if nf else None, nf, max_det,
+                                     ctypes.c_float(MAX_WH), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(counts.data_ptr()),
+                                     ctypes.c_void_p(idx.data_ptr()) if want_idx else None, None, _stream(dev)), "decode_nms")
+    return out, counts, idx
