@@ -42,9 +42,9 @@ def make_state_dict(seed, classes=80, anchor_num=3):
             sd[name] = torch.from_numpy((0.2 * rs.randn(*shape)).astype(np.float32))
         elif len(shape) == 4:
             fan_in = shape[1] * shape[2] * shape[3]
-            sd[name] = torch.from_numpy((rs.randn(*shape) * np.sqrt(2.0 / fan_in)).astype(np.float32))
+            sd[name] = torch.from_numpy((rs.randn(*shape) * np.sqrt(1.0 / fan_in)).astype(np.float32))
         elif name.endswith(".weight"):      # BN gamma
-            sd[name] = torch.from_numpy(rs.uniform(0.6, 1.4, shape).astype(np.float32))
+            sd[name] = torch.from_numpy(rs.uniform(0.5, 1.2, shape).astype(np.float32))
         else:                               # BN beta / conv bias
             sd[name] = torch.from_numpy((0.2 * rs.randn(*shape)).astype(np.float32))
     return sd
