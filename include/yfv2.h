@@ -116,6 +116,16 @@ YFV2_API int yfv2_detect_u8_host(yfv2_plan* plan, const uint8_t* x_host, const v
                         float* out_host, int* counts_host, void* workspace, void* stream);
 YFV2_API size_t yfv2_detect_workspace_bytes(const yfv2_plan* plan, int max_det);
 
+/* ---- test hook: dense NCHW copy of an intermediate tensor of the last forward -------------------------
+ * which: 0 stem output, 1..16 ShuffleV2 block outputs in execution order (logical channel order, i.e. what
+ * the reference's block returns), 17 S2, 18 S3, 19..22 mid-head scratch (cls2, reg2, cls3, reg3).
+ * dims4 receives [N,C,h,w]; out may be NULL to query dims only. */
+/* run only the first n fused stages of forward (1 = stem, 2..17 = blocks; 0 = everything): block outputs
+ * share recycled planes, so a mid-network tensor is only intact right after its producer ran */
+YFV2_API int yfv2_debug_stop_after(yfv2_plan* plan, int n_stages);
+YFV2_API int yfv2_debug_gather(const yfv2_plan* plan, const void* workspace, int which, float* out, int* dims4,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,16 +29,17 @@ __device__ __forceinline__ void pw_inplace(float* __restrict__ X, int RS, int WS
     constexpr int NS = K / NSPLIT;
     const int groups = W / PPT;
     const int cnt = nrows * groups;
-    const int items = cnt * NSPLIT;
     const float* scale = wpw + K * K;
     const float* shift = scale + K;
-    for (int base = 0; base < items; base += NT) {
-        const int q = base + threadIdx.x;
-        bool active = q < items;
-        int h = 0, rr = 0, x0 = 0;
+    // All NSPLIT output slices of a pixel group run in the SAME round: the stores of a round overwrite the
+    // inputs of exactly the pixel groups that round has finished reading.
+    constexpr int PPR = NT / NSPLIT;
+    const int h = threadIdx.x / PPR;
+    for (int base = 0; base < cnt; base += PPR) {
+        const int r = base + (threadIdx.x - h * PPR);
+        bool active = r < cnt && h < NSPLIT;
+        int rr = 0, x0 = 0;
         if (active) {
-            h = q / cnt;
-            const int r = q - h * cnt;
             rr = r / groups;
             x0 = (r - rr * groups) * PPT;
             const int gr = gr0 + rr;

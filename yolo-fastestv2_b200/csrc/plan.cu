@@ -81,6 +81,17 @@ __global__ void pack_dw_kernel(const float* __restrict__ w, int Cn, int KK, int 
     }
 }
 
+// dense NCHW copy of a logical tensor (tests / debugging only)
+__global__ void gather_kernel(Planes P, ChanTab tab, int Cn, float* __restrict__ out, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int HW = P.H * P.W;
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % Cn);
+    const int n = (int)(i / ((long long)HW * Cn));
+    out[i] = plane_ptr(P, n, tab.c[c])[p];
+}
+
 struct Cursor {           // walks parameters / BN layers in state_dict order
     const float* const* params;
     const float* const* bn;
@@ -104,7 +115,9 @@ struct yfv2_plan {
     int blk_K[kNumBlocks], blk_stride[kNumBlocks], blk_res[kNumBlocks];   // res = index of OUTPUT resolution
     ChanTab tin[kNumBlocks], tout[kNumBlocks];
     ChanTab c2, c3;
+    ChanTab logical[kNumBlocks];       // logical channel order of each block's output (debug gather)
     int launches;
+    int debug_stop;                    // test hook: run only the first debug_stop fused stages (0 = all)
 };
 
 namespace {
@@ -158,6 +171,7 @@ void build_tables(yfv2_plan* p) {
                 L.insert(L.end(), freep.begin(), freep.end());
                 freep = mainin;
             }
+            for (size_t i = 0; i < L.size(); ++i) p->logical[bi].c[i] = (unsigned short)L[i];
         }
         if (st == 1) for (int i = 0; i < 96; ++i) p->c2.c[i] = (unsigned short)L[i];
         if (st == 2) for (int i = 0; i < 192; ++i) p->c3.c[i] = (unsigned short)L[i];
@@ -330,6 +344,7 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
 
     StemArgs st{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
     TRY(launch_stem(st, s));
+    if (p->debug_stop == 1) return YFV2_OK;
     for (int b = 0; b < kNumBlocks; ++b) {
         ShuffleArgs a;
         a.K = p->blk_K[b]; a.stride = p->blk_stride[b]; a.N = p->N;
@@ -338,6 +353,7 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
         a.tin = p->tin[b]; a.tout = p->tout[b];
         a.wpack = pk + p->pk_block[b];
         TRY(launch_shuffle(a, s));
+        if (p->debug_stop == b + 2) return YFV2_OK;
     }
     FpnArgs f;
     f.N = p->N;
@@ -421,5 +437,31 @@ extern "C" int yfv2_detect_u8_host(yfv2_plan* p, const uint8_t* x_host, const vo
                         4096.0f, out_dev, counts_dev, nullptr, nullptr, stream));
     YFV2_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)p->N * max_det * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
     YFV2_CUDA(cudaMemcpyAsync(counts_host, counts_dev, (size_t)p->N * sizeof(int), cudaMemcpyDeviceToHost, s));
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_debug_stop_after(yfv2_plan* p, int n_stages) {
+    if (!p || n_stages < 0) { set_error("debug_stop_after: bad argument"); return YFV2_EINVAL; }
+    p->debug_stop = n_stages;
+    return YFV2_OK;
+}
+
+// ---- debug: dense NCHW copy of an intermediate tensor ------------------------------------------------------
+extern "C" int yfv2_debug_gather(const yfv2_plan* p, const void* workspace, int which, float* out, int* dims4, void* stream) {
+    if (!p || !workspace || !dims4) { set_error("debug_gather: null argument"); return YFV2_EINVAL; }
+    float* ws = (float*)workspace;
+    Planes P; ChanTab tab; int Cn;
+    for (int i = 0; i < kMaxCh; ++i) tab.c[i] = (unsigned short)i;
+    if (which == 0) { P = pool_planes(p, ws, 0); Cn = 24; }
+    else if (which >= 1 && which <= kNumBlocks) { const int b = which - 1; P = pool_planes(p, ws, p->blk_res[b]); Cn = 2 * p->blk_K[b]; tab = p->logical[b]; }
+    else if (which == 17) { P = flat_planes(p, ws, p->off_s2, 2); Cn = kFpnDepth; }
+    else if (which == 18) { P = flat_planes(p, ws, p->off_s3, 3); Cn = kFpnDepth; }
+    else if (which >= 19 && which <= 22) { const int i = which - 19; P = flat_planes(p, ws, p->off_t[i], i < 2 ? 2 : 3); Cn = kFpnDepth; }
+    else { set_error("debug_gather: unknown tensor id %d", which); return YFV2_EINVAL; }
+    dims4[0] = p->N; dims4[1] = Cn; dims4[2] = P.H; dims4[3] = P.W;
+    if (!out) return YFV2_OK;
+    const long long total = (long long)p->N * Cn * P.H * P.W;
+    gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, tab, Cn, out, total);
+    YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }

@@ -51,6 +51,9 @@ PROTOTYPES = {
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_detect_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
+    "yfv2_debug_stop_after": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yfv2_debug_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
 }
 
 
@@ -172,6 +175,19 @@ class Plan:
             _check(fn(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(self.packed.data_ptr()), _ptr_array(preds),
                       ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)), "forward")
         return preds
+
+    def debug_stop_after(self, n_stages):
+        _check(lib().yfv2_debug_stop_after(self._h, n_stages), "debug_stop_after")
+
+    def debug_gather(self, which):
+        """Dense NCHW copy of an intermediate tensor of the last forward (test hook, see yfv2.h)."""
+        dims = (ctypes.c_int * 4)()
+        _check(lib().yfv2_debug_gather(self._h, ctypes.c_void_p(self.workspace.data_ptr()), which, None, dims, None), "debug_gather")
+        out = torch.empty(tuple(dims), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(lib().yfv2_debug_gather(self._h, ctypes.c_void_p(self.workspace.data_ptr()), which,
+                                           ctypes.c_void_p(out.data_ptr()), dims, _stream(self.device)), "debug_gather")
+        return out
 
     def detect_u8_host(self, x_host, anchors, conf_thres, iou_thres, out_host, counts_host, max_det=MAX_DET):
         """Whole step from pinned host uint8 images to pinned host detections (asynchronous)."""
