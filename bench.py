@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — images/s of the Yolo-FastestV2 hot path (forward + decode + NMS) on B200.
+
+Workload (BASELINE.json configs[1]): batch 256 of 352x352 synthetic images per GPU, random-init weights
+(seed 1, BN running stats (0,1)), decode + NMS(conf 0.001, iou 0.4) — the regime where every one of the 1815
+candidates passes the confidence filter and the 300-detection cap is hit.
+
+  python bench.py [--gpus N --steps K --warmup W]          our CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference ...                      the CPU restatement of the reference (oracle/) on host cores
+
+One JSON line on stdout (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
+through yfv2_detect_u8_host with pinned HOST uint8 images in and pinned HOST detections out, copies inside the
+timed region; `roofline` = the slowest fused kernel against the measured HBM peak; `cpu_baseline` = the oracle
+port on the host cores (a bounded sample).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+BATCH, SIDE, CLASSES, ANCHORS = 256, 352, 80, 3
+CONF, IOU = 0.001, 0.4
+METRIC = "images/sec 352x352 fwd+decode+NMS"
+STAGE_NAMES = (["stem"] + ["stage2.%d" % i for i in range(4)] + ["stage3.%d" % i for i in range(8)]
+               + ["stage4.%d" % i for i in range(4)] + ["fpn.S3", "fpn.S2", "heads2.a", "heads2.b", "heads3.a", "heads3.b"])
+
+
+def cfg():
+    import synth
+    return synth.coco_cfg(SIDE, SIDE, CLASSES)
+
+
+def random_state_dict():
+    """Detector default PyTorch init under seed 1, BN running stats left at (0,1) (SURVEY 8d config[1])."""
+    import yfv2  # noqa: F401
+    import model.detector as det
+    import contextlib
+    torch.manual_seed(1)
+    with contextlib.redirect_stdout(sys.stderr):          # the mirror prints "load param..." like the reference
+        m = det.Detector(CLASSES, ANCHORS, True)
+    return m, {k: v.clone() for k, v in m.state_dict().items()}
+
+
+def algorithmic_bytes_per_image(H=SIDE, W=SIDE, A=ANCHORS, C=CLASSES):
+    """one read of each fused unit's input + one write of its output, fp32, weights excluded."""
+    hw = lambda s: (H // s) * (W // s)
+    b = [4 * (3 * H * W + 24 * hw(4))]
+    for st, (K, s_in, s_out, rep) in enumerate(((24, 4, 8, 4), (48, 8, 16, 8), (96, 16, 32, 4))):
+        b.append(4 * (K * hw(s_in) + 2 * K * hw(s_out)))
+        b += [4 * (2 * K * hw(s_out)) * 2] * (rep - 1)
+    b.append(4 * (192 * hw(32) + 72 * hw(32)))
+    b.append(4 * ((192 * hw(32) + 96 * hw(16)) + 72 * hw(16)))
+    for s in (16, 32):
+        b.append(2 * 4 * (72 * hw(s) + 72 * hw(s)))                              # first halves of both heads
+        b.append(2 * 4 * (72 * hw(s) + 72 * hw(s)) + 4 * (2 * 72 + 5 * A + C) * hw(s))   # second halves + output convs
+    return b
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:      # NVML missing: report nothing rather than guess
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(min_seconds, batch, threads=None, steps=None, warmup=1):
+    """Times the oracle port (forward + decode + NMS) on the host cores.  Returns (img/s, info)."""
+    from oracle import net as onet, post as opost
+    import synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    _, sd = random_state_dict()
+    c = cfg()
+    x = synth.make_images(1, batch, SIDE, SIDE)
+
+    def step():
+        with torch.no_grad():
+            preds = onet.forward(sd, x)
+        dets = opost.decode(preds, c)
+        return opost.nms(dets, CONF, IOU)
+
+    for _ in range(warmup):
+        step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and el >= min_seconds):
+            break
+    return n * batch / el, {"cores": threads, "kind": "port", "ms_per_step": 1e3 * el / n,
+                            "sample": "%d step(s) of batch %d @%dx%d: oracle forward+decode+NMS(%g,%g), torch %d threads + C NMS"
+                                      % (n, batch, SIDE, SIDE, CONF, IOU, threads)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch = 16
+    v, info = cpu_reference_throughput(0, batch, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batch=256 352x352 inference (backbone+FPN+head+decode+NMS), random weights; "
+                                   "CPU arm runs bounded steps of batch %d" % batch},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import yfv2  # noqa: F401
+    import yfv2_engine as eng
+    import synth
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    model, _ = random_state_dict()
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(1 + rank)
+    x = torch.rand(BATCH, 3, SIDE, SIDE, generator=g).to(dev)            # 380 MB fp32 > L2 (126 MB)
+    c = cfg()
+    plan = model._plan_for(x)
+    preds = plan.alloc_preds()
+    anchors = eng.anchors_array(c)
+    import ctypes
+    out = torch.empty((BATCH, eng.MAX_DET, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((BATCH,), dtype=torch.int32, device=dev)
+    L = eng.lib()
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        plan.forward(x, preds)
+        rc = L.yfv2_decode_nms(eng._ptr_array(preds), BATCH, SIDE, SIDE, ANCHORS, CLASSES, anchors, ctypes.c_float(CONF),
+                               ctypes.c_double(IOU), None, 0, eng.MAX_DET, ctypes.c_float(eng.MAX_WH),
+                               ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(counts.data_ptr()), None, None,
+                               ctypes.c_void_p(stream.cuda_stream))
+        if rc:
+            raise RuntimeError(L.yfv2_last_error())
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * BATCH * args.steps / (ms / 1e3)
+    kept = int(counts.sum().item())
+
+    # ---- e2e: pinned host uint8 in, pinned host detections out, double buffered on two streams ------------
+    e2e = None
+    try:
+        nbuf = 2
+        plans = [eng.Plan(dev, BATCH, SIDE, SIDE, ANCHORS, CLASSES, detect_max_det=eng.MAX_DET) for _ in range(nbuf)]
+        params, bn = model._weight_tensors()
+        for p_ in plans:
+            p_.pack(params, bn)
+        xs = [(torch.rand(BATCH, 3, SIDE, SIDE, generator=g) * 255).to(torch.uint8).pin_memory() for _ in range(nbuf)]
+        outs = [torch.empty((BATCH, eng.MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+        cnts = [torch.empty((BATCH,), dtype=torch.int32).pin_memory() for _ in range(nbuf)]
+        streams = [torch.cuda.Stream(dev) for _ in range(nbuf)]
+
+        def e2e_step(i):
+            b = i % nbuf
+            with torch.cuda.stream(streams[b]):
+                plans[b].detect_u8_host(xs[b], anchors, CONF, IOU, outs[b], cnts[b])
+
+        for i in range(max(args.warmup, 3)):
+            e2e_step(i)
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for st_ in streams:
+            st_.wait_event(s0)
+        for i in range(args.steps):
+            e2e_step(i)
+        for st_ in streams:
+            ev = torch.cuda.Event()
+            ev.record(st_)
+            stream.wait_event(ev)
+        s1 = torch.cuda.Event(enable_timing=True)
+        s1.record(stream)
+        barrier()
+        ms2 = s0.elapsed_time(s1)
+        t2 = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+        e2e = {"value": world * BATCH * args.steps / (float(t2.item()) / 1e3), "unit": "images/s",
+               "h2d_bytes_per_step": xs[0].numel(), "d2h_bytes_per_step": outs[0].numel() * 4 + cnts[0].numel() * 4,
+               "api": "yfv2_detect_u8_host (pinned uint8 NCHW in, [N,300,6]+counts out), 2 streams double-buffered",
+               "kept_check": int(sum(int(c_.sum()) for c_ in cnts))}
+        del plans
+    except Exception as ex:     # never hide a failure: report it in the line
+        e2e = {"value": None, "error": repr(ex)}
+
+    # ---- per-stage timing (rank 0) -> roofline of the slowest fused kernel ------------------------------------
+    roof, stages = None, None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bpi = algorithmic_bytes_per_image()
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)       # 256 MB > L2
+        reps = max(3, min(args.steps, 10))
+        plan.forward(x, preds)
+        stages = []
+        for st in range(len(STAGE_NAMES)):
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                plan.forward_range(x, preds, st, st + 1)
+                b.record(stream)
+                b.synchronize()
+                tot += a.elapsed_time(b)
+            us = 1e3 * tot / reps
+            gbs = bpi[st] * BATCH / (us * 1e-6) / 1e9
+            stages.append({"stage": STAGE_NAMES[st], "us": round(us, 2), "alg_MB": round(bpi[st] * BATCH / 1e6, 2),
+                           "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)})
+        top = max(stages, key=lambda s: s["us"])
+        bb = [s for s in stages if s["stage"].startswith(("stem", "stage"))]
+        bb_bytes = sum(s["alg_MB"] for s in bb) * 1e6
+        bb_us = sum(s["us"] for s in bb)
+        roof = {"bound": "hbm", "kernel": top["stage"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": top["frac"], "traffic": None, "peak_source": peak_src, "timing": "CUDA events, L2 flushed before each launch",
+                "backbone": {"achieved": round(bb_bytes / (bb_us * 1e-6) / 1e9, 1), "frac": round(bb_bytes / (bb_us * 1e-6) / 1e9 / peak, 4),
+                             "us": round(bb_us, 1)}}
+        del flush
+
+    cpu = None
+    if rank == 0 and world == 1:
+        v, info = cpu_reference_throughput(12.0, 16)
+        cpu = {"value": v, "unit": "images/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "batch=256 352x352 inference (backbone+FPN+head+decode+NMS) per GPU, random weights, "
+                                       "NMS conf 0.001 iou 0.4", "global_batch": world * BATCH, "parallelism": "replicas x%d, no collective" % world,
+                           "l2": "inputs (380 MB fp32 per step) exceed the 126 MB L2; activations stream through it"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (plan.forward_launches + 1),
+                "kept_boxes_per_step": kept, "roofline": roof, "cpu_baseline": cpu, "stages": stages}
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -109,3 +109,24 @@ def test_batch_invariance_at_full_size():
     one = m(x[3:4])
     for p, q in zip(one, small):
         assert torch.equal(p[0], q[3])
+
+
+def test_every_fused_stage_against_reference_taps(golden_dir):
+    """Stage-by-stage parity: run the forward one fused kernel at a time (yfv2_forward_range) and compare each
+    block output, in the reference's logical channel order, with the activations hooked out of the real
+    reference (tests/golden/net_small.npz tap_*)."""
+    g = dict(np.load(os.path.join(golden_dir, "net_small.npz")))
+    m = make_model(synth.make_state_dict(11))
+    x = synth.make_images(12, 2, 64, 96).cuda()
+    preds = m(x)
+    plan = next(iter(m._plans.values()))
+    names = ["stem"] + ["stage2.%d" % i for i in range(4)] + ["stage3.%d" % i for i in range(8)] + ["stage4.%d" % i for i in range(4)]
+    for st, name in enumerate(names):
+        plan.forward_range(x, preds, st, st + 1)
+        got = plan.debug_gather(st).cpu().numpy()
+        np.testing.assert_allclose(got, g["tap_" + name], err_msg=name, **TOL)
+    plan.forward_range(x, preds, 17, 23)
+    np.testing.assert_allclose(plan.debug_gather(18).cpu().numpy(), g["tap_S3"], **TOL)
+    np.testing.assert_allclose(plan.debug_gather(17).cpu().numpy(), g["tap_S2"], **TOL)
+    for i, p in enumerate(preds):
+        np.testing.assert_allclose(p.cpu().numpy(), g["pred%d" % i], **TOL)

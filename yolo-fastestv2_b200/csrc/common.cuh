@@ -143,7 +143,7 @@ struct FpnArgs {
     const float* w3;          // PW 192->72
     const float* w2;          // PW 288->72  (k order: up(C3) 0..191, C2 192..287; fpn.py:58)
 };
-int launch_fpn(const FpnArgs& a, cudaStream_t s);
+int launch_fpn(const FpnArgs& a, int which /*0: S3, 1: S2*/, cudaStream_t s);
 
 struct HeadArgs {
     int N, A, C;
@@ -155,7 +155,7 @@ struct HeadArgs {
     const float* w_out_oc;    // PW 72->(A+C): obj rows first, then cls rows
     float* reg; float* obj; float* cls;   // dense NCHW outputs for this level
 };
-int launch_heads(const HeadArgs& a, cudaStream_t s);
+int launch_heads(const HeadArgs& a, int half /*0: first dw+pw, 1: second dw+pw + output convs*/, cudaStream_t s);
 size_t head_pack_floats();
 
 }  // namespace yfv2

@@ -62,16 +62,15 @@ fpn_pw_kernel(Planes A, ChanTab ta, Planes B, ChanTab tb, Planes out, const floa
 }
 }  // namespace
 
-int launch_fpn(const FpnArgs& a, cudaStream_t s) {
-    {
+int launch_fpn(const FpnArgs& a, int which, cudaStream_t s) {
+    if (which == 0) {
         auto kern = fpn_pw_kernel<192, 0, 0>;
         const size_t bytes = pw_pack_floats(192, NOUT) * sizeof(float);
         YFV2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         const int total = a.N * a.s3.H * a.s3.W;
         kern<<<(total + NT - 1) / NT, NT, bytes, s>>>(a.c3, a.t3, a.c3, a.t3, a.s3, a.w3, total);
         YFV2_LAUNCH_CHECK();
-    }
-    {
+    } else {
         auto kern = fpn_pw_kernel<192, 96, 1>;
         const size_t bytes = pw_pack_floats(288, NOUT) * sizeof(float);
         YFV2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

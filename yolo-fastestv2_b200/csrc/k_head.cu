@@ -153,7 +153,7 @@ int run_half(const HeadIO& io, const ChanTab& ident, int N, int TR, size_t bytes
 
 size_t head_pack_floats() { return 2 * (size_t)HALF_FLOATS; }
 
-int launch_heads(const HeadArgs& a, cudaStream_t s) {
+int launch_heads(const HeadArgs& a, int half, cudaStream_t s) {
     const int H = a.s.H, W = a.s.W;
     const int Moc = a.A + a.C, Mreg = 4 * a.A;
     const size_t wout_max = (size_t)pw_pack_floats(CH, Moc > Mreg ? Moc : Mreg);
@@ -177,9 +177,9 @@ int launch_heads(const HeadArgs& a, cudaStream_t s) {
     io.in[0] = a.s; io.in[1] = a.s;
     io.out[0] = a.t_cls; io.out[1] = a.t_reg;
     io.w[0] = a.w_cls; io.w[1] = a.w_reg;
-    int rc = nsplit == 3 ? run_half<3, false>(io, ident, a.N, TR, bytes(TR, false), s)
-                         : run_half<2, false>(io, ident, a.N, TR, bytes(TR, false), s);
-    if (rc) return rc;
+    if (half == 0)
+        return nsplit == 3 ? run_half<3, false>(io, ident, a.N, TR, bytes(TR, false), s)
+                           : run_half<2, false>(io, ident, a.N, TR, bytes(TR, false), s);
 
     io.in[0] = a.t_cls; io.in[1] = a.t_reg;
     io.w[0] = a.w_cls + HALF_FLOATS; io.w[1] = a.w_reg + HALF_FLOATS;

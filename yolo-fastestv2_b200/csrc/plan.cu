@@ -117,7 +117,6 @@ struct yfv2_plan {
     ChanTab c2, c3;
     ChanTab logical[kNumBlocks];       // logical channel order of each block's output (debug gather)
     int launches;
-    int debug_stop;                    // test hook: run only the first debug_stop fused stages (0 = all)
 };
 
 namespace {
@@ -225,7 +224,7 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     p->pk_out_reg = pk; pk += pw_pack_floats(kFpnDepth, 4 * A);
     p->pk_out_oc = pk; pk += pw_pack_floats(kFpnDepth, A + C);
     p->pk_floats = pk;
-    p->launches = 1 + kNumBlocks + 2 + 4;
+    p->launches = 1 + kNumBlocks + 2 + 4;   // == kNumStages
     *out = p;
     return YFV2_OK;
 }
@@ -335,26 +334,16 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
 }
 
 namespace {
+constexpr int kNumStages = 1 + kNumBlocks + 2 + 4;   // stem, 16 blocks, fpn S3, fpn S2, 2 levels x 2 head halves
+
+// Runs fused stages [first, last) of the forward; each stage is exactly one kernel launch.
 int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, float* const preds[6], void* workspace,
-                 cudaStream_t s) {
+                 int first, int last, cudaStream_t s) {
     if (!p || !x || !packed || !preds || !workspace) { set_error("forward: null argument"); return YFV2_EINVAL; }
     for (int i = 0; i < 6; ++i) if (!preds[i]) { set_error("forward: null output %d", i); return YFV2_EINVAL; }
+    if (first < 0 || last > kNumStages || first > last) { set_error("forward: bad stage range [%d,%d)", first, last); return YFV2_EINVAL; }
     float* ws = (float*)workspace;
     const float* pk = (const float*)packed;
-
-    StemArgs st{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
-    TRY(launch_stem(st, s));
-    if (p->debug_stop == 1) return YFV2_OK;
-    for (int b = 0; b < kNumBlocks; ++b) {
-        ShuffleArgs a;
-        a.K = p->blk_K[b]; a.stride = p->blk_stride[b]; a.N = p->N;
-        a.out = pool_planes(p, ws, p->blk_res[b]);
-        a.in = a.stride == 2 ? pool_planes(p, ws, p->blk_res[b] - 1) : a.out;
-        a.tin = p->tin[b]; a.tout = p->tout[b];
-        a.wpack = pk + p->pk_block[b];
-        TRY(launch_shuffle(a, s));
-        if (p->debug_stop == b + 2) return YFV2_OK;
-    }
     FpnArgs f;
     f.N = p->N;
     f.c3 = pool_planes(p, ws, 3); f.t3 = p->c3;
@@ -362,32 +351,53 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
     f.s3 = flat_planes(p, ws, p->off_s3, 3);
     f.s2 = flat_planes(p, ws, p->off_s2, 2);
     f.w3 = pk + p->pk_fpn3; f.w2 = pk + p->pk_fpn2;
-    TRY(launch_fpn(f, s));
-    for (int lv = 0; lv < 2; ++lv) {
-        HeadArgs h;
-        h.N = p->N; h.A = p->A; h.C = p->C;
-        h.s = lv ? f.s3 : f.s2;
-        h.t_cls = flat_planes(p, ws, p->off_t[2 * lv], 2 + lv);
-        h.t_reg = flat_planes(p, ws, p->off_t[2 * lv + 1], 2 + lv);
-        h.w_cls = pk + p->pk_head[2 * lv];
-        h.w_reg = pk + p->pk_head[2 * lv + 1];
-        h.w_out_reg = pk + p->pk_out_reg;
-        h.w_out_oc = pk + p->pk_out_oc;
-        h.reg = preds[3 * lv]; h.obj = preds[3 * lv + 1]; h.cls = preds[3 * lv + 2];
-        TRY(launch_heads(h, s));
+    for (int st = first; st < last; ++st) {
+        if (st == 0) {
+            StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
+            TRY(launch_stem(a, s));
+        } else if (st <= kNumBlocks) {
+            const int b = st - 1;
+            ShuffleArgs a;
+            a.K = p->blk_K[b]; a.stride = p->blk_stride[b]; a.N = p->N;
+            a.out = pool_planes(p, ws, p->blk_res[b]);
+            a.in = a.stride == 2 ? pool_planes(p, ws, p->blk_res[b] - 1) : a.out;
+            a.tin = p->tin[b]; a.tout = p->tout[b];
+            a.wpack = pk + p->pk_block[b];
+            TRY(launch_shuffle(a, s));
+        } else if (st <= kNumBlocks + 2) {
+            TRY(launch_fpn(f, st - kNumBlocks - 1, s));
+        } else {
+            const int q = st - kNumBlocks - 3, lv = q >> 1, half = q & 1;
+            HeadArgs h;
+            h.N = p->N; h.A = p->A; h.C = p->C;
+            h.s = lv ? f.s3 : f.s2;
+            h.t_cls = flat_planes(p, ws, p->off_t[2 * lv], 2 + lv);
+            h.t_reg = flat_planes(p, ws, p->off_t[2 * lv + 1], 2 + lv);
+            h.w_cls = pk + p->pk_head[2 * lv];
+            h.w_reg = pk + p->pk_head[2 * lv + 1];
+            h.w_out_reg = pk + p->pk_out_reg;
+            h.w_out_oc = pk + p->pk_out_oc;
+            h.reg = preds[3 * lv]; h.obj = preds[3 * lv + 1]; h.cls = preds[3 * lv + 2];
+            TRY(launch_heads(h, half, s));
+        }
     }
     return YFV2_OK;
 }
 }  // namespace
 
+extern "C" int yfv2_forward_range(yfv2_plan* p, const void* x, int is_u8, const void* packed, float* const preds[6],
+                                  void* workspace, int first, int last, void* stream) {
+    return forward_impl(p, x, is_u8, packed, preds, workspace, first, last, (cudaStream_t)stream);
+}
+
 extern "C" int yfv2_forward(yfv2_plan* p, const float* x, const void* packed, float* const preds[6], void* workspace,
                             void* stream) {
-    return forward_impl(p, x, 0, packed, preds, workspace, (cudaStream_t)stream);
+    return forward_impl(p, x, 0, packed, preds, workspace, 0, kNumStages, (cudaStream_t)stream);
 }
 
 extern "C" int yfv2_forward_u8(yfv2_plan* p, const uint8_t* x, const void* packed, float* const preds[6], void* workspace,
                                void* stream) {
-    return forward_impl(p, x, 1, packed, preds, workspace, (cudaStream_t)stream);
+    return forward_impl(p, x, 1, packed, preds, workspace, 0, kNumStages, (cudaStream_t)stream);
 }
 
 // ---- whole step with host buffers ---------------------------------------------------------------------------
@@ -432,17 +442,11 @@ extern "C" int yfv2_detect_u8_host(yfv2_plan* p, const uint8_t* x_host, const vo
     float* out_dev = (float*)(ws + L.off_out);
     int* counts_dev = (int*)(ws + L.off_counts);
     YFV2_CUDA(cudaMemcpyAsync(x_dev, x_host, (size_t)p->N * 3 * p->H * p->W, cudaMemcpyHostToDevice, s));
-    TRY(forward_impl(p, x_dev, 1, packed, preds, ws, s));
+    TRY(forward_impl(p, x_dev, 1, packed, preds, ws, 0, kNumStages, s));
     TRY(yfv2_decode_nms(preds, p->N, p->H, p->W, p->A, p->C, anchors_host, conf_thres, iou_thres, nullptr, 0, max_det,
                         4096.0f, out_dev, counts_dev, nullptr, nullptr, stream));
     YFV2_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)p->N * max_det * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));
     YFV2_CUDA(cudaMemcpyAsync(counts_host, counts_dev, (size_t)p->N * sizeof(int), cudaMemcpyDeviceToHost, s));
-    return YFV2_OK;
-}
-
-extern "C" int yfv2_debug_stop_after(yfv2_plan* p, int n_stages) {
-    if (!p || n_stages < 0) { set_error("debug_stop_after: bad argument"); return YFV2_EINVAL; }
-    p->debug_stop = n_stages;
     return YFV2_OK;
 }
 

@@ -51,7 +51,8 @@ PROTOTYPES = {
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_detect_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
-    "yfv2_debug_stop_after": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yfv2_forward_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _c_void_pp,
+                                          ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "yfv2_debug_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
 }
@@ -176,8 +177,13 @@ class Plan:
                       ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)), "forward")
         return preds
 
-    def debug_stop_after(self, n_stages):
-        _check(lib().yfv2_debug_stop_after(self._h, n_stages), "debug_stop_after")
+    def forward_range(self, x, preds, first, last):
+        """Runs fused stages [first,last) only (see yfv2.h); x, preds as in forward()."""
+        with torch.cuda.device(self.device):
+            _check(lib().yfv2_forward_range(self._h, ctypes.c_void_p(x.data_ptr()), int(x.dtype == torch.uint8),
+                                            ctypes.c_void_p(self.packed.data_ptr()), _ptr_array(preds),
+                                            ctypes.c_void_p(self.workspace.data_ptr()), first, last, _stream(self.device)),
+                   "forward_range")
 
     def debug_gather(self, which):
         """Dense NCHW copy of an intermediate tensor of the last forward (test hook, see yfv2.h)."""
