@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, nm in names.items():
@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

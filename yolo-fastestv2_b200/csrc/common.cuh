@@ -87,6 +87,15 @@ __device__ __forceinline__ void fma_row(const float* __restrict__ wrow, const fl
     }
 }
 
+// ---- cp.async (LDGSTS) helpers: fire-and-forget global->shared copies, no register staging ----------------
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // Stage rows [gr0, gr0+nrows) of the K planes listed in tab into X[k][rr*WS + PAD + x]; WS = W + 2*PAD.
 // Out-of-image rows and the PAD columns are written as zeros (the zero padding of the next conv).
 template <int K, int PAD, int NTHREADS>
@@ -102,12 +111,14 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ X, int RS, int WS
             const float* src = plane_ptr(P, n, tab.c[k]) + (long long)gr * W;
             for (int cc = lane; cc < WS; cc += 32) {
                 const int x = cc - PAD;
-                dst[cc] = (x >= 0 && x < W) ? __ldg(src + x) : 0.f;
+                if (x >= 0 && x < W) cp_async4(dst + cc, src + x);      // many loads in flight per warp
+                else dst[cc] = 0.f;
             }
         } else {
             for (int cc = lane; cc < WS; cc += 32) dst[cc] = 0.f;
         }
     }
+    cp_async_wait_all();      // the caller's __syncthreads() publishes the tile
 }
 
 int sm_count();

@@ -35,18 +35,44 @@ stem_kernel(const void* __restrict__ xin, Planes out, const float* __restrict__ 
     const int tid = threadIdx.x;
 
     copy_to_smem(s_w, wpack, kStemPackFloats);
-    for (int i = tid; i < 3 * IT_H * IT_W; i += STEM_THREADS) {
-        const int c = i / (IT_H * IT_W);
-        const int rem = i - c * (IT_H * IT_W);
-        const int r = rem / IT_W, q = rem - r * IT_W;
-        const int iy = iy0 + r, ix = ix0 + q;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            const size_t off = (((size_t)n * 3 + c) * H + iy) * W + ix;
-            if (U8) v = __fdiv_rn((float)__ldg(reinterpret_cast<const uint8_t*>(xin) + off), 255.0f);
-            else    v = __ldg(reinterpret_cast<const float*>(xin) + off);
+    // input patch: fp32 goes through cp.async (all loads in flight at once); uint8 is converted on the fly
+    // in batches of 8 independent loads per thread
+    if (!U8) {
+        for (int i = tid; i < 3 * IT_H * IT_W; i += STEM_THREADS) {
+            const int c = i / (IT_H * IT_W);
+            const int rem = i - c * (IT_H * IT_W);
+            const int r = rem / IT_W, q = rem - r * IT_W;
+            const int iy = iy0 + r, ix = ix0 + q;
+            float* dst = &s_in[(c * IT_H + r) * IT_WS + q];
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                cp_async4(dst, reinterpret_cast<const float*>(xin) + ((((size_t)n * 3 + c) * H + iy) * W + ix));
+            else
+                *dst = 0.f;
         }
-        s_in[(c * IT_H + r) * IT_WS + q] = v;
+        cp_async_wait_all();
+    } else {
+        constexpr int TOT = 3 * IT_H * IT_W, UNR = 8;
+        for (int i0 = tid; i0 < TOT; i0 += STEM_THREADS * UNR) {
+            uint8_t v[UNR];
+            int sidx[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int i = i0 + u * STEM_THREADS;
+                v[u] = 0; sidx[u] = -1;
+                if (i < TOT) {
+                    const int c = i / (IT_H * IT_W);
+                    const int rem = i - c * (IT_H * IT_W);
+                    const int r = rem / IT_W, q = rem - r * IT_W;
+                    const int iy = iy0 + r, ix = ix0 + q;
+                    sidx[u] = (c * IT_H + r) * IT_WS + q;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                        v[u] = __ldg(reinterpret_cast<const uint8_t*>(xin) + ((((size_t)n * 3 + c) * H + iy) * W + ix));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (sidx[u] >= 0) s_in[sidx[u]] = __fdiv_rn((float)v[u], 255.0f);
+        }
     }
     __syncthreads();
 
