@@ -132,6 +132,11 @@ YFV2_API int yfv2_forward_range(yfv2_plan* plan, const void* x, int is_u8, const
 YFV2_API int yfv2_debug_gather(const yfv2_plan* plan, const void* workspace, int which, float* out, int* dims4,
                                void* stream);
 
+/* ---- test hook: one pointwise contraction on the tcgen05 engine (3xTF32), out[n][p] = sum_k w[n][k]*x[k][p] ----
+ * x: [K][P], w: [N][K], out: [N][P], pack_ws: scratch of at least 2*roundup(N,16)*roundup(K,8) floats. */
+YFV2_API int yfv2_debug_pw_tc(const float* x, const float* w, float* out, float* pack_ws, int K, int N, int P,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "yfv2_detect_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
     "yfv2_forward_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _c_void_pp,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "yfv2_debug_pw_tc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "yfv2_debug_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
 }
@@ -267,3 +269,17 @@ def decode_nms(preds, cfg, conf_thres=0.3, iou_thres=0.45, classes=None, max_det
                                      ctypes.c_float(MAX_WH), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(counts.data_ptr()),
                                      ctypes.c_void_p(idx.data_ptr()) if want_idx else None, None, _stream(dev)), "decode_nms")
     return out, counts, idx
+
+
+def debug_pw_tc(x, w):
+    """out[n][p] = sum_k w[n][k] * x[k][p] on the tcgen05 3xTF32 engine (test hook)."""
+    _require_cuda(x, "x"); _require_cuda(w, "w")
+    K, P = x.shape
+    N = w.shape[0]
+    out = torch.empty((N, P), dtype=torch.float32, device=x.device)
+    ws = torch.empty((2 * ((N + 15) // 16 * 16) * ((K + 7) // 8 * 8),), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib().yfv2_debug_pw_tc(ctypes.c_void_p(x.contiguous().data_ptr()), ctypes.c_void_p(w.contiguous().data_ptr()),
+                                      ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), K, N, P, _stream(x.device)),
+               "debug_pw_tc")
+    return out
