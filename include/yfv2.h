@@ -117,16 +117,18 @@ YFV2_API int yfv2_detect_u8_host(yfv2_plan* plan, const uint8_t* x_host, const v
 YFV2_API size_t yfv2_detect_workspace_bytes(const yfv2_plan* plan, int max_det);
 
 /* ---- stage-granular forward (profiling / tests) ---------------------------------------------------------
- * Runs fused stages [first,last) of the forward, one kernel launch per stage: 0 stem, 1..16 ShuffleV2 blocks,
- * 17 FPN S3, 18 FPN S2, 19/20 level-2 heads (first / second half + output convs), 21/22 level-3 heads.
- * bench.py times single stages with it; the block outputs of a stage are only intact until a later stage
- * recycles their planes. */
-#define YFV2_NUM_STAGES 23
+ * A forward is yfv2_plan_forward_launches() fused stages, one kernel launch each; yfv2_plan_stage_name(i) names
+ * them ("stem", "stage2.0", ..., "stage4.1/pw1", "stage4.1/dwpw", "fpn.S3", "fpn.S2", "heads2.a", ...).
+ * yfv2_forward_range runs stages [first,last) (last < 0: to the end).  bench.py times single stages with it; a
+ * block's output is only intact until a later stage recycles its planes.  The stage list depends on the
+ * engine: tcgen05 kernels by default, the FFMA kernels when the environment has YFV2_ENGINE=ffma at
+ * plan-creation time. */
+YFV2_API const char* yfv2_plan_stage_name(const yfv2_plan* plan, int i);
 YFV2_API int yfv2_forward_range(yfv2_plan* plan, const void* x, int is_u8, const void* packed, float* const preds[6],
                                 void* workspace, int first, int last, void* stream);
 
 /* ---- test hook: dense NCHW copy of an intermediate tensor of the last forward -------------------------
- * which: 0 stem output, 1..16 ShuffleV2 block outputs in execution order (logical channel order, i.e. what
+ * which: 0 stem output, 1..16 ShuffleV2 block outputs in network order (logical channel order, i.e. what
  * the reference's block returns), 17 S2, 18 S3, 19..22 mid-head scratch (cls2, reg2, cls3, reg3).
  * dims4 receives [N,C,h,w]; out may be NULL to query dims only. */
 YFV2_API int yfv2_debug_gather(const yfv2_plan* plan, const void* workspace, int which, float* out, int* dims4,

@@ -121,12 +121,28 @@ def test_every_fused_stage_against_reference_taps(golden_dir):
     preds = m(x)
     plan = next(iter(m._plans.values()))
     names = ["stem"] + ["stage2.%d" % i for i in range(4)] + ["stage3.%d" % i for i in range(8)] + ["stage4.%d" % i for i in range(4)]
-    for st, name in enumerate(names):
-        plan.forward_range(x, preds, st, st + 1)
-        got = plan.debug_gather(st).cpu().numpy()
+    stages = plan.stage_names                    # a block may be more than one launch ("stage4.1/pw1", "stage4.1/dwpw")
+    done = 0
+    for bi, name in enumerate(names):
+        last = max(i for i, sn in enumerate(stages) if sn.split("/")[0] == name)
+        plan.forward_range(x, preds, done, last + 1)
+        done = last + 1
+        got = plan.debug_gather(bi).cpu().numpy()
         np.testing.assert_allclose(got, g["tap_" + name], err_msg=name, **TOL)
-    plan.forward_range(x, preds, 17, 23)
+    plan.forward_range(x, preds, done, len(stages))
     np.testing.assert_allclose(plan.debug_gather(18).cpu().numpy(), g["tap_S3"], **TOL)
     np.testing.assert_allclose(plan.debug_gather(17).cpu().numpy(), g["tap_S2"], **TOL)
     for i, p in enumerate(preds):
         np.testing.assert_allclose(p.cpu().numpy(), g["pred%d" % i], **TOL)
+
+
+def test_ffma_engine_still_matches(golden_dir, monkeypatch):
+    """The FFMA kernels stay available (YFV2_ENGINE=ffma at plan creation) as the cross-check of the tcgen05 path."""
+    monkeypatch.setenv("YFV2_ENGINE", "ffma")
+    g = dict(np.load(os.path.join(golden_dir, "net_352.npz")))
+    m = make_model(synth.make_state_dict(21))
+    preds = m(synth.make_images(22, 1, 352, 352).cuda())
+    plan = next(iter(m._plans.values()))
+    assert "stage4.1" in plan.stage_names and "stage4.1/pw1" not in plan.stage_names
+    for i, p in enumerate(preds):
+        np.testing.assert_allclose(p.cpu().numpy(), g["pred%d" % i], err_msg="pred%d" % i, **TOL)

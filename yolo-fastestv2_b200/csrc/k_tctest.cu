@@ -55,7 +55,7 @@ tc_pw_test_kernel(const float* __restrict__ x, const float* __restrict__ pack, f
     __syncthreads();
     if (tid == 0) {
         tc::fence_after_sync();
-        tc::issue_pw<KP, NP>(tbase + 2 * KP, tbase, tbase + KP, tc::smem_u32(sB), tc::smem_u32(sB + NP * KP), false);
+        tc::issue_pw<KP, NP, KP>(tbase + 2 * KP, tbase, tbase + KP, tc::smem_u32(sB), tc::smem_u32(sB + NP * KP), 0, false);
         tc::mma_commit(&mbar);
     }
     tc::mbar_wait(&mbar, 0);

@@ -10,7 +10,10 @@
 #include <new>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace yfv2 {
 
@@ -81,6 +84,19 @@ __global__ void pack_dw_kernel(const float* __restrict__ w, int Cn, int KK, int 
     }
 }
 
+// Tensor-core pack of a pointwise layer (tc.cuh): tf32 hi/lo split, UMMA K-major no-swizzle core-matrix tiling.
+__global__ void pack_tc_kernel(const float* __restrict__ w, int Nout, int K, int NP, int KP, int n_off, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nout * KP) return;
+    const int n = i / KP, k = i - n * KP;
+    const float v = (k < K) ? w[n * K + k] : 0.f;
+    const uint32_t hi = tc::tf32_rna(v);
+    const uint32_t lo = tc::tf32_rna(v - __uint_as_float(hi));
+    const int o = tc::tc_b_index(n_off + n, k, KP);
+    dst[o] = __uint_as_float(hi);
+    dst[NP * KP + o] = __uint_as_float(lo);
+}
+
 // dense NCHW copy of a logical tensor (tests / debugging only)
 __global__ void gather_kernel(Planes P, ChanTab tab, int Cn, float* __restrict__ out, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,6 +133,13 @@ struct yfv2_plan {
     ChanTab c2, c3;
     ChanTab logical[kNumBlocks];       // logical channel order of each block's output (debug gather)
     int launches;
+    // tensor-core engine
+    int engine;                        // 0 = FFMA kernels (k_shuffle/k_fpn/k_head), 1 = tcgen05 kernels (k_tcnet)
+    size_t tk_blk[kNumBlocks][3];      // tc packs per block: [0]=pw1 [1]=pw2 [2]=proj pw (stride-2 only)
+    size_t tk_fpn3, tk_fpn2, tk_head[4][2], tk_out_oc, tk_out_reg;
+    ChanTab t96;                       // scratch plane ids for the K=96 blocks' pw1 output
+    int n_stages;
+    struct Stage { int kind, a, b; char name[24]; } stages[64];
 };
 
 namespace {
@@ -198,7 +221,7 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     if (!p) { set_error("plan_create: out of host memory"); return YFV2_ENOMEM; }
     memset(p, 0, sizeof(*p));
     p->device = device; p->N = N; p->H = H; p->W = W; p->A = A; p->C = C; p->training = training;
-    const int pools[4] = {24, 72, 144, 288};
+    const int pools[4] = {24, 72, 144 + 96, 288 + 96};   // +96: scratch planes for the K=96 blocks' pw1 output
     size_t off = 0;
     for (int r = 0; r < 4; ++r) {
         p->h[r] = H >> (r + 2); p->w[r] = W >> (r + 2);
@@ -223,8 +246,43 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     for (int i = 0; i < 4; ++i) { p->pk_head[i] = pk; pk += align_up(head_pack_floats(), 4); }
     p->pk_out_reg = pk; pk += pw_pack_floats(kFpnDepth, 4 * A);
     p->pk_out_oc = pk; pk += pw_pack_floats(kFpnDepth, A + C);
+    // tensor-core packs
+    for (int b = 0; b < kNumBlocks; ++b) {
+        const int K = p->blk_K[b], NP = tc::tc_round(K, 16);
+        const int n = p->blk_stride[b] == 2 ? 3 : 2;
+        for (int i = 0; i < n; ++i) { p->tk_blk[b][i] = pk; pk += align_up(2 * (size_t)NP * K + 2 * NP, 4); }
+    }
+    p->tk_fpn3 = pk; pk += align_up(2 * 80 * 192 + 160, 4);
+    p->tk_fpn2 = pk; pk += align_up(2 * 80 * 288 + 160, 4);
+    for (int i = 0; i < 4; ++i) for (int h = 0; h < 2; ++h) { p->tk_head[i][h] = pk; pk += align_up(2 * 80 * 72 + 160, 4); }
+    p->tk_out_oc = pk; pk += align_up(2 * 96 * 80 + 192, 4);
+    p->tk_out_reg = pk; pk += align_up(2 * 96 * 80 + 192, 4);
     p->pk_floats = pk;
-    p->launches = 1 + kNumBlocks + 2 + 4;   // == kNumStages
+    for (int i = 0; i < 96; ++i) p->t96.c[i] = 0;   // filled per use (pool-specific offset)
+
+    const char* eng = getenv("YFV2_ENGINE");
+    p->engine = (eng && !strcmp(eng, "ffma")) ? 0 : 1;
+    if (p->engine == 1 && (A + C > 96 || 4 * A > 96)) p->engine = 0;    // chained output-conv tile is 96 wide
+    auto add = [&](int kind, int a, int b, const char* fmt, int x, int y) {
+        yfv2_plan::Stage& st = p->stages[p->n_stages++];
+        st.kind = kind; st.a = a; st.b = b;
+        snprintf(st.name, sizeof(st.name), fmt, x, y);
+    };
+    add(0, 0, 0, "stem", 0, 0);
+    for (int b = 0, st = 0, rep = 0; b < kNumBlocks; ++b) {
+        if (p->engine == 0) add(1, b, 0, "stage%d.%d", st + 2, rep);
+        else if (p->blk_K[b] < 96) add(p->blk_stride[b] == 2 ? 11 : 10, b, 0, "stage%d.%d", st + 2, rep);
+        else { add(12, b, 0, "stage%d.%d/pw1", st + 2, rep); add(13, b, 0, "stage%d.%d/dwpw", st + 2, rep); }
+        if (++rep == kStageRepeats[st]) { rep = 0; ++st; }
+    }
+    if (p->engine == 0) {
+        add(2, 0, 0, "fpn.S3", 0, 0); add(2, 1, 0, "fpn.S2", 0, 0);
+        for (int lv = 0; lv < 2; ++lv) { add(3, lv, 0, "heads%d.a", lv + 2, 0); add(3, lv, 1, "heads%d.b", lv + 2, 0); }
+    } else {
+        add(14, 1, 0, "fpn.S3", 0, 0); add(14, 2, 0, "fpn.S2", 0, 0);
+        for (int lv = 0; lv < 2; ++lv) { add(15, lv, 0, "heads%d.a", lv + 2, 0); add(15, lv, 1, "heads%d.b", lv + 2, 0); }
+    }
+    p->launches = p->n_stages;
     *out = p;
     return YFV2_OK;
 }
@@ -246,6 +304,11 @@ extern "C" int yfv2_plan_packed_bytes(const yfv2_plan* p, size_t* bytes) {
     return YFV2_OK;
 }
 
+extern "C" const char* yfv2_plan_stage_name(const yfv2_plan* p, int i) {
+    if (!p || i < 0 || i >= p->n_stages) return nullptr;
+    return p->stages[i].name;
+}
+
 extern "C" int yfv2_plan_forward_launches(const yfv2_plan* p, int* n) {
     if (!p || !n) { set_error("forward_launches: null argument"); return YFV2_EINVAL; }
     *n = p->launches;
@@ -254,7 +317,9 @@ extern "C" int yfv2_plan_forward_launches(const yfv2_plan* p, int* n) {
 
 namespace {
 
-int pack_pw(Cursor& cur, bool bn, bool bias, int Nout, int K, float* pack, int Np, int n_off, cudaStream_t s) {
+struct TcDst { float* dst; int NP, KP; };
+
+int pack_pw(Cursor& cur, bool bn, bool bias, int Nout, int K, float* pack, int Np, int n_off, cudaStream_t s, TcDst tcd = {nullptr, 0, 0}) {
     const float* w = cur.params[cur.p];
     const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr, *bi = nullptr;
     if (bn) { g = cur.params[cur.p + 1]; b = cur.params[cur.p + 2]; m = cur.bn[2 * cur.b]; v = cur.bn[2 * cur.b + 1]; cur.p += 3; cur.b += 1; }
@@ -265,6 +330,15 @@ int pack_pw(Cursor& cur, bool bn, bool bias, int Nout, int K, float* pack, int N
     pack_pw_kernel<<<(total + 255) / 256, 256, 0, s>>>(w, Nout, K, g, b, m, v, bi, pack, Np, n_off, pack + (size_t)K * Np,
                                                         pack + (size_t)K * Np + Np);
     YFV2_LAUNCH_CHECK();
+    if (tcd.dst) {
+        // same layer for the tcgen05 engine: Bhi | Blo tiles, then scale[NP] | shift[NP] (zero padded by the memset)
+        pack_tc_kernel<<<(Nout * tcd.KP + 255) / 256, 256, 0, s>>>(w, Nout, K, tcd.NP, tcd.KP, n_off, tcd.dst);
+        YFV2_LAUNCH_CHECK();
+        float* aff = tcd.dst + 2 * (size_t)tcd.NP * tcd.KP;
+        // reuse the affine part of pack_pw_kernel: Nout*1 "weights" written to a scratch-free position is avoided by K=0
+        pack_pw_kernel<<<(Nout + 255) / 256, 256, 0, s>>>(w, Nout, 0, g, b, m, v, bi, aff, tcd.NP, n_off, aff, aff + tcd.NP);
+        YFV2_LAUNCH_CHECK();
+    }
     return YFV2_OK;
 }
 
@@ -296,36 +370,42 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
         const int K = p->blk_K[b];
         float* d = pk + p->pk_block[b];
         const int pwn = pw_pack_floats(K, K), dwn = dw3_pack_floats(K);
+        const int NPk = tc::tc_round(K, 16);
+        const TcDst t1{pk + p->tk_blk[b][0], NPk, K}, t2{pk + p->tk_blk[b][1], NPk, K}, tp{pk + p->tk_blk[b][2], NPk, K};
         if (p->blk_stride[b] == 2) {
             // state_dict order: branch_main (pw1, dw, pw2) then branch_proj (dw, pw); pack order DWp|PWp|PW1|DW|PW2
-            TRY(pack_pw(cur, true, false, K, K, d + dwn + pwn, K, 0, s));
+            TRY(pack_pw(cur, true, false, K, K, d + dwn + pwn, K, 0, s, t1));
             TRY(pack_dw(cur, K, 3, d + dwn + 2 * pwn, s));
-            TRY(pack_pw(cur, true, false, K, K, d + 2 * dwn + 2 * pwn, K, 0, s));
+            TRY(pack_pw(cur, true, false, K, K, d + 2 * dwn + 2 * pwn, K, 0, s, t2));
             TRY(pack_dw(cur, K, 3, d, s));
-            TRY(pack_pw(cur, true, false, K, K, d + dwn, K, 0, s));
+            TRY(pack_pw(cur, true, false, K, K, d + dwn, K, 0, s, tp));
         } else {
-            TRY(pack_pw(cur, true, false, K, K, d, K, 0, s));
+            TRY(pack_pw(cur, true, false, K, K, d, K, 0, s, t1));
             TRY(pack_dw(cur, K, 3, d + pwn, s));
-            TRY(pack_pw(cur, true, false, K, K, d + pwn + dwn, K, 0, s));
+            TRY(pack_pw(cur, true, false, K, K, d + pwn + dwn, K, 0, s, t2));
         }
     }
     // fpn: conv1x1_2, conv1x1_3, cls_head_2, reg_head_2, reg_head_3, cls_head_3 (fpn.py:35-49 registration order)
-    TRY(pack_pw(cur, true, false, kFpnDepth, 288, pk + p->pk_fpn2, kFpnDepth, 0, s));
-    TRY(pack_pw(cur, true, false, kFpnDepth, 192, pk + p->pk_fpn3, kFpnDepth, 0, s));
+    TRY(pack_pw(cur, true, false, kFpnDepth, 288, pk + p->pk_fpn2, kFpnDepth, 0, s, TcDst{pk + p->tk_fpn2, 80, 288}));
+    TRY(pack_pw(cur, true, false, kFpnDepth, 192, pk + p->pk_fpn3, kFpnDepth, 0, s, TcDst{pk + p->tk_fpn3, 80, 192}));
     const int head_order[4] = {0, 1, 3, 2};     // pk_head index: 0 cls2, 1 reg2, 2 cls3, 3 reg3
     for (int i = 0; i < 4; ++i) {
         float* d = pk + p->pk_head[head_order[i]];
         const int dwn = dw5_pack_floats(kFpnDepth), pwn = pw_pack_floats(kFpnDepth, kFpnDepth);
+        const int hi_ = head_order[i];
         TRY(pack_dw(cur, kFpnDepth, 5, d, s));
-        TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + dwn, kFpnDepth, 0, s));
+        TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + dwn, kFpnDepth, 0, s, TcDst{pk + p->tk_head[hi_][0], 80, 72}));
         TRY(pack_dw(cur, kFpnDepth, 5, d + dwn + pwn, s));
-        TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + 2 * dwn + pwn, kFpnDepth, 0, s));
+        TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + 2 * dwn + pwn, kFpnDepth, 0, s, TcDst{pk + p->tk_head[hi_][1], 80, 72}));
     }
     // output_reg_layers, output_obj_layers, output_cls_layers (detector.py:17-19); obj and cls share one pack
-    TRY(pack_pw(cur, false, true, 4 * p->A, kFpnDepth, pk + p->pk_out_reg, round4(4 * p->A), 0, s));
+    // the chained output convs contract over the 80-column (72 real) feature tile of the head's second pointwise
+    const bool tc_ok = p->engine == 1;
+    TRY(pack_pw(cur, false, true, 4 * p->A, kFpnDepth, pk + p->pk_out_reg, round4(4 * p->A), 0, s,
+                tc_ok ? TcDst{pk + p->tk_out_reg, 96, 80} : TcDst{nullptr, 0, 0}));
     const int Moc = round4(p->A + p->C);
-    TRY(pack_pw(cur, false, true, p->A, kFpnDepth, pk + p->pk_out_oc, Moc, 0, s));
-    TRY(pack_pw(cur, false, true, p->C, kFpnDepth, pk + p->pk_out_oc, Moc, p->A, s));
+    TRY(pack_pw(cur, false, true, p->A, kFpnDepth, pk + p->pk_out_oc, Moc, 0, s, tc_ok ? TcDst{pk + p->tk_out_oc, 96, 80} : TcDst{nullptr, 0, 0}));
+    TRY(pack_pw(cur, false, true, p->C, kFpnDepth, pk + p->pk_out_oc, Moc, p->A, s, tc_ok ? TcDst{pk + p->tk_out_oc, 96, 80} : TcDst{nullptr, 0, 0}));
     if (cur.p != YFV2_NUM_PARAMS || cur.b != YFV2_NUM_BN) {
         set_error("pack_weights: internal walk consumed %d params / %d BN layers", cur.p, cur.b);
         return YFV2_EINVAL;
@@ -333,17 +413,31 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
     return YFV2_OK;
 }
 
-namespace {
-constexpr int kNumStages = 1 + kNumBlocks + 2 + 4;   // stem, 16 blocks, fpn S3, fpn S2, 2 levels x 2 head halves
+namespace yfv2 {
+int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout, const float* w1, const float* wdw, const float* w2,
+                 int N, cudaStream_t s);
+int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin, const ChanTab& tout, const float* wdwp, const float* wp,
+                 const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s);
+int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, const ChanTab& tb, const Planes& out, const ChanTab& tout,
+                 const float* wpack, int N, cudaStream_t s);
+int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
+                     const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
+int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
+                    const float* wout_oc, const float* wout_reg, float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s);
+}
 
+namespace {
 // Runs fused stages [first, last) of the forward; each stage is exactly one kernel launch.
 int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, float* const preds[6], void* workspace,
                  int first, int last, cudaStream_t s) {
     if (!p || !x || !packed || !preds || !workspace) { set_error("forward: null argument"); return YFV2_EINVAL; }
     for (int i = 0; i < 6; ++i) if (!preds[i]) { set_error("forward: null output %d", i); return YFV2_EINVAL; }
-    if (first < 0 || last > kNumStages || first > last) { set_error("forward: bad stage range [%d,%d)", first, last); return YFV2_EINVAL; }
+    if (last < 0) last = p->n_stages;
+    if (first < 0 || last > p->n_stages || first > last) { set_error("forward: bad stage range [%d,%d)", first, last); return YFV2_EINVAL; }
     float* ws = (float*)workspace;
     const float* pk = (const float*)packed;
+    ChanTab ident;
+    for (int i = 0; i < kMaxCh; ++i) ident.c[i] = (unsigned short)i;
     FpnArgs f;
     f.N = p->N;
     f.c3 = pool_planes(p, ws, 3); f.t3 = p->c3;
@@ -351,12 +445,15 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
     f.s3 = flat_planes(p, ws, p->off_s3, 3);
     f.s2 = flat_planes(p, ws, p->off_s2, 2);
     f.w3 = pk + p->pk_fpn3; f.w2 = pk + p->pk_fpn2;
-    for (int st = first; st < last; ++st) {
-        if (st == 0) {
+    for (int si = first; si < last; ++si) {
+        const yfv2_plan::Stage& st = p->stages[si];
+        const int b = st.a;
+        switch (st.kind) {
+        case 0: {
             StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
             TRY(launch_stem(a, s));
-        } else if (st <= kNumBlocks) {
-            const int b = st - 1;
+        } break;
+        case 1: {
             ShuffleArgs a;
             a.K = p->blk_K[b]; a.stride = p->blk_stride[b]; a.N = p->N;
             a.out = pool_planes(p, ws, p->blk_res[b]);
@@ -364,10 +461,10 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             a.tin = p->tin[b]; a.tout = p->tout[b];
             a.wpack = pk + p->pk_block[b];
             TRY(launch_shuffle(a, s));
-        } else if (st <= kNumBlocks + 2) {
-            TRY(launch_fpn(f, st - kNumBlocks - 1, s));
-        } else {
-            const int q = st - kNumBlocks - 3, lv = q >> 1, half = q & 1;
+        } break;
+        case 2: TRY(launch_fpn(f, st.a, s)); break;
+        case 3: case 15: {
+            const int lv = st.a, half = st.b;
             HeadArgs h;
             h.N = p->N; h.A = p->A; h.C = p->C;
             h.s = lv ? f.s3 : f.s2;
@@ -378,7 +475,58 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             h.w_out_reg = pk + p->pk_out_reg;
             h.w_out_oc = pk + p->pk_out_oc;
             h.reg = preds[3 * lv]; h.obj = preds[3 * lv + 1]; h.cls = preds[3 * lv + 2];
-            TRY(launch_heads(h, half, s));
+            if (st.kind == 3) { TRY(launch_heads(h, half, s)); break; }
+            // tensor-core heads: DW pack = first 72*28 floats of each half of the FFMA head pack
+            const size_t half_off = (size_t)half * (dw5_pack_floats(kFpnDepth) + pw_pack_floats(kFpnDepth, kFpnDepth));
+            const float* wdw[2] = {h.w_cls + half_off, h.w_reg + half_off};
+            const float* wpw[2] = {pk + p->tk_head[2 * lv][half], pk + p->tk_head[2 * lv + 1][half]};
+            TRY(tc_launch_heads(half, h.s, h.t_cls, h.t_reg, wdw, wpw, pk + p->tk_out_oc, pk + p->tk_out_reg, h.reg, h.obj, h.cls,
+                                p->A, p->C, p->N, s));
+        } break;
+        case 10: {   // tc fused stride-1 block
+            const int K = p->blk_K[b];
+            const float* d = pk + p->pk_block[b];
+            TRY(tc_launch_s1(K, pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b], pk + p->tk_blk[b][0],
+                             d + pw_pack_floats(K, K), pk + p->tk_blk[b][1], p->N, s));
+        } break;
+        case 11: {   // tc fused stride-2 block
+            const int K = p->blk_K[b];
+            const float* d = pk + p->pk_block[b];
+            const int dwn = dw3_pack_floats(K), pwn = pw_pack_floats(K, K);
+            TRY(tc_launch_s2(K, pool_planes(p, ws, p->blk_res[b] - 1), pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b],
+                             d, pk + p->tk_blk[b][2], pk + p->tk_blk[b][0], d + dwn + 2 * pwn, pk + p->tk_blk[b][1], p->N, s));
+        } break;
+        case 12: case 13: {   // K=96 blocks: pw1 (global -> scratch planes), then dw3x3 -> pw2 (+ proj branch when stride 2)
+            const int stride = p->blk_stride[b];
+            const Planes out = pool_planes(p, ws, p->blk_res[b]);
+            const Planes in = stride == 2 ? pool_planes(p, ws, p->blk_res[b] - 1) : out;
+            ChanTab t96;
+            const int base = stride == 2 ? 144 : 288;           // scratch planes live in the INPUT resolution's pool
+            for (int i = 0; i < 96; ++i) t96.c[i] = (unsigned short)(base + i);
+            if (st.kind == 12) {
+                TRY(tc_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s));
+            } else {
+                const float* d = pk + p->pk_block[b];
+                const int dwn = dw3_pack_floats(96), pwn = pw_pack_floats(96, 96);
+                if (stride == 1) {
+                    const Planes ins[1] = {in}; const ChanTab tins[1] = {t96}; const Planes outs[1] = {out}; const ChanTab touts[1] = {p->tout[b]};
+                    const float* wdw[1] = {d + pwn}; const float* wpw[1] = {pk + p->tk_blk[b][1]};
+                    TRY(tc_launch_dwpw96(1, 1, ins, tins, outs, touts, wdw, wpw, p->N, s));
+                } else {
+                    ChanTab tmain;
+                    for (int i = 0; i < 96; ++i) tmain.c[i] = p->tout[b].c[96 + i];
+                    const Planes ins[2] = {in, in}; const ChanTab tins[2] = {p->tin[b], t96};
+                    const Planes outs[2] = {out, out}; const ChanTab touts[2] = {p->tout[b], tmain};
+                    const float* wdw[2] = {d, d + dwn + 2 * pwn}; const float* wpw[2] = {pk + p->tk_blk[b][2], pk + p->tk_blk[b][1]};
+                    TRY(tc_launch_dwpw96(2, 2, ins, tins, outs, touts, wdw, wpw, p->N, s));
+                }
+            }
+        } break;
+        case 14: {   // tc FPN reducers
+            if (st.a == 1) { TRY(tc_launch_pw(1, f.c3, f.t3, f.c3, f.t3, f.s3, ident, pk + p->tk_fpn3, p->N, s)); }
+            else { TRY(tc_launch_pw(2, f.c3, f.t3, f.c2, f.t2, f.s2, ident, pk + p->tk_fpn2, p->N, s)); }
+        } break;
+        default: set_error("forward: unknown stage kind %d", st.kind); return YFV2_EINVAL;
         }
     }
     return YFV2_OK;
@@ -392,12 +540,12 @@ extern "C" int yfv2_forward_range(yfv2_plan* p, const void* x, int is_u8, const 
 
 extern "C" int yfv2_forward(yfv2_plan* p, const float* x, const void* packed, float* const preds[6], void* workspace,
                             void* stream) {
-    return forward_impl(p, x, 0, packed, preds, workspace, 0, kNumStages, (cudaStream_t)stream);
+    return forward_impl(p, x, 0, packed, preds, workspace, 0, -1, (cudaStream_t)stream);
 }
 
 extern "C" int yfv2_forward_u8(yfv2_plan* p, const uint8_t* x, const void* packed, float* const preds[6], void* workspace,
                                void* stream) {
-    return forward_impl(p, x, 1, packed, preds, workspace, 0, kNumStages, (cudaStream_t)stream);
+    return forward_impl(p, x, 1, packed, preds, workspace, 0, -1, (cudaStream_t)stream);
 }
 
 // ---- whole step with host buffers ---------------------------------------------------------------------------
@@ -442,7 +590,7 @@ extern "C" int yfv2_detect_u8_host(yfv2_plan* p, const uint8_t* x_host, const vo
     float* out_dev = (float*)(ws + L.off_out);
     int* counts_dev = (int*)(ws + L.off_counts);
     YFV2_CUDA(cudaMemcpyAsync(x_dev, x_host, (size_t)p->N * 3 * p->H * p->W, cudaMemcpyHostToDevice, s));
-    TRY(forward_impl(p, x_dev, 1, packed, preds, ws, 0, kNumStages, s));
+    TRY(forward_impl(p, x_dev, 1, packed, preds, ws, 0, -1, s));
     TRY(yfv2_decode_nms(preds, p->N, p->H, p->W, p->A, p->C, anchors_host, conf_thres, iou_thres, nullptr, 0, max_det,
                         4096.0f, out_dev, counts_dev, nullptr, nullptr, stream));
     YFV2_CUDA(cudaMemcpyAsync(out_host, out_dev, (size_t)p->N * max_det * 6 * sizeof(float), cudaMemcpyDeviceToHost, s));

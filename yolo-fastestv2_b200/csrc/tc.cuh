@@ -118,17 +118,19 @@ __host__ __device__ constexpr int tc_round(int x, int m) { return (x + m - 1) / 
 __host__ __device__ constexpr int tc_pack_floats(int K, int N) { return 2 * tc_round(N, 16) * tc_round(K, 8) + 2 * tc_round(N, 16); }
 __host__ __device__ constexpr int tc_b_index(int n, int k, int KP) { return (n >> 3) * (KP * 8) + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
 
-// Issue the 3*KP/8 MMAs of one PW for one 128-row tile.  One thread calls this.
-//   a_hi / a_lo / d: TMEM addresses (lane 0) of the operand column blocks; b_hi / b_lo: shared addresses of the packs.
-template <int KP, int NP>
+// Issue the 3*KC/8 MMAs of one K-chunk of a PW for one 128-row tile.  One thread calls this.
+//   a_hi / a_lo / d: TMEM addresses (lane 0) of the operand column blocks (the chunk's KC columns each);
+//   b_hi / b_lo: shared addresses of the FULL packs (KPFULL columns per row); chunk_k0 = first K index of the chunk.
+template <int KC, int NP, int KPFULL>
 __device__ __forceinline__ void issue_pw(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_smem, uint32_t b_lo_smem,
-                                         bool accumulate_first) {
+                                         int chunk_k0, bool accumulate_first) {
     constexpr uint32_t idesc = make_idesc_tf32(128, NP);
-    constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
+    constexpr uint32_t LBO = 128, SBO = (KPFULL / 4) * 128;
 #pragma unroll
-    for (int s = 0; s < KP / 8; ++s) {
-        const uint64_t bh = make_b_desc(b_hi_smem + s * 256, LBO, SBO);
-        const uint64_t bl = make_b_desc(b_lo_smem + s * 256, LBO, SBO);
+    for (int s = 0; s < KC / 8; ++s) {
+        const uint32_t koff = (uint32_t)(chunk_k0 / 8 + s) * 256;
+        const uint64_t bh = make_b_desc(b_hi_smem + koff, LBO, SBO);
+        const uint64_t bl = make_b_desc(b_lo_smem + koff, LBO, SBO);
         mma_tf32_ts(d, a_lo + 8 * s, bh, idesc, (s > 0 || accumulate_first) ? 1u : 0u);   // small terms first
         mma_tf32_ts(d, a_hi + 8 * s, bl, idesc, 1u);
         mma_tf32_ts(d, a_hi + 8 * s, bh, idesc, 1u);

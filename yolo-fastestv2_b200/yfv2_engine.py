@@ -51,6 +51,7 @@ PROTOTYPES = {
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_detect_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
+    "yfv2_plan_stage_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
     "yfv2_forward_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _c_void_pp,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "yfv2_debug_pw_tc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
@@ -130,6 +131,7 @@ class Plan:
         n = ctypes.c_int()
         _check(L.yfv2_plan_forward_launches(self._h, ctypes.byref(n)), "forward_launches")
         self.forward_launches = n.value
+        self.stage_names = [L.yfv2_plan_stage_name(self._h, i).decode() for i in range(n.value)]
         self.packed_version = None
 
     def __del__(self):
