@@ -21,16 +21,40 @@ namespace {
 
 using namespace tc;
 
-constexpr int kTmemCols = 512;
+// ---------------------------------------------------------------------------------------------------------
+// Engine.  A CTA = G warpgroups (128 threads, thread <-> pixel <-> TMEM lane).  The A operand streams through TMEM
+// in 8-channel chunks, double buffered, and there is NO dedicated issuer: whichever of the group's four warps is
+// the last to finish storing a chunk issues that chunk's MMAs (an acq_rel shared-memory counter decides), so no
+// warp ever waits for an MMA to be *issued*:
+//   every warp:  (wait empty[buf]) -> split 8 channels -> tcgen05.st hi/lo -> wait::st, fence -> counter++
+//   4th arriver: 3 x tcgen05.mma (K=8) -> tcgen05.commit -> empty[buf]   (+ commit -> dfull after the tile's last chunk)
+//   every warp:  wait dfull -> tcgen05.ld D -> epilogue
+// A group needs only 32 + NP TMEM columns whatever K is; the MMAs of a chunk overlap the depthwise / load work of
+// the following chunks and of the other groups.  Two such CTAs fit on an SM (each allocates 256 of the 512 columns).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTmemCols = 256;          // per CTA; every kernel here allocates the same amount (two CTAs fill an SM's 512)
+constexpr int kACols = 32;             // 2 buffers x (8 hi + 8 lo)
+
+struct Pipe {                          // per group, in shared memory
+    uint64_t empty[2], dfull;
+    uint32_t arrivals[2];
+    uint32_t pad_[2];
+};
 
 struct Grp {
-    uint32_t tcol;     // TMEM address (lane 0) of this group's column block
-    uint32_t tlane;    // same, at this warp's lane quarter
-    uint64_t* mbar;
-    uint32_t parity;
-    int bar_id;
-    int gtid;          // thread index inside the group, 0..127
+    uint32_t tcol;                     // TMEM address (lane 0) of the group's column block
+    uint32_t tlane;                    // same, at this warp's lane quarter
+    Pipe* pipe;
+    uint32_t chunk;                    // chunks produced so far (buffer = chunk & 1, use index = chunk >> 1)
+    uint32_t dparity;
+    int gtid;                          // thread index inside the group, 0..127
 };
+
+__device__ __forceinline__ uint32_t atom_add_acq_rel(uint32_t* addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+    return old;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -42,74 +66,85 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// One pointwise contraction for the group's current tile, K processed in KP/KC chunks (KC = KP: one shot).
-//   load(k0, a[8])  : fill channels k0..k0+7 of this thread's pixel (zeros for padding channels / invalid pixels)
-//   epi(n0, d[16])  : consume outputs n0..n0+15 of this thread's pixel
-// TMEM columns of the group: A_hi [0,KC), A_lo [KC,2KC), D [2KC, 2KC+NP).
-template <int KP, int NP, int KC, class Loader, class Epi>
-__device__ __forceinline__ void pw_tile_c(Grp& g, uint32_t b_hi, uint32_t b_lo, Loader&& load, Epi&& epi) {
-    static_assert(KP % KC == 0 && KC % 8 == 0, "chunking");
-#pragma unroll 1
-    for (int c = 0; c < KP / KC; ++c) {
-        if (c > 0) {                         // the MMAs of the previous chunk must have consumed A before it is overwritten
-            mbar_wait(g.mbar, g.parity);
-            g.parity ^= 1u;
+// Hand chunk c (8 channels of this thread's pixel) of a KP->NP contraction to the tensor core.
+//   b_hi / b_lo: shared addresses of the weight pack; `last`: this is the tile's final chunk.
+template <int KP, int NP>
+__device__ __forceinline__ void put_chunk(Grp& g, const float (&a)[8], int c, uint32_t b_hi, uint32_t b_lo) {
+    const uint32_t buf = g.chunk & 1u, use = g.chunk >> 1;
+    if (use > 0) mbar_wait(&g.pipe->empty[buf], (use - 1) & 1u);     // the MMAs that read this buffer last time are done
+    fence_after_sync();
+    store_a8(g.tlane + buf * 16, 8, a);
+    wait_st();
+    fence_before_sync();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t old = atom_add_acq_rel(&g.pipe->arrivals[buf], 1u);
+        if ((old & 3u) == 3u) {                                      // all four warps of the group have stored this chunk
             fence_after_sync();
-        }
-#pragma unroll
-        for (int k0 = 0; k0 < KC; k0 += 8) {
-            float a[8];
-            load(c * KC + k0, a);
-            store_a8(g.tlane + k0, KC, a);
-        }
-        wait_st();
-        fence_before_sync();
-        group_bar(g.bar_id, 128);
-        if (g.gtid == 0) {
-            fence_after_sync();
-            issue_pw<KC, NP, KP>(g.tcol + 2 * KC, g.tcol, g.tcol + KC, b_hi, b_lo, c * KC, c > 0);
-            mma_commit(g.mbar);
+            constexpr uint32_t idesc = make_idesc_tf32(128, NP);
+            constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
+            const uint32_t a_hi = g.tcol + buf * 16, a_lo = a_hi + 8, d = g.tcol + kACols;
+            const uint64_t bh = make_b_desc(b_hi + c * 256, LBO, SBO);
+            const uint64_t bl = make_b_desc(b_lo + c * 256, LBO, SBO);
+            mma_tf32_ts(d, a_lo, bh, idesc, c > 0 ? 1u : 0u);        // small terms first
+            mma_tf32_ts(d, a_hi, bl, idesc, 1u);
+            mma_tf32_ts(d, a_hi, bh, idesc, 1u);
+            mma_commit(&g.pipe->empty[buf]);
+            if (c == KP / 8 - 1) mma_commit(&g.pipe->dfull);
         }
     }
-    mbar_wait(g.mbar, g.parity);
-    g.parity ^= 1u;
+    __syncwarp();
+    ++g.chunk;
+}
+// Collect the NP output columns of this thread's pixel.
+template <int NP, class Epi>
+__device__ __forceinline__ void get_tile(Grp& g, Epi&& epi) {
+    mbar_wait(&g.pipe->dfull, g.dparity);
+    g.dparity ^= 1u;
     fence_after_sync();
 #pragma unroll
     for (int n0 = 0; n0 < NP; n0 += 16) {
         float d[16];
-        tmem_ld16(g.tlane + 2 * KC + n0, d);
+        tmem_ld16(g.tlane + kACols + n0, d);
         wait_ld();
         epi(n0, d);
     }
-    fence_before_sync();
-    group_bar(g.bar_id, 128);      // D and A may be overwritten by the next tile from here on
+    // the next put_chunk's fence::before_thread_sync + counter increment orders these reads before D is overwritten
 }
 template <int KP, int NP, class Loader, class Epi>
 __device__ __forceinline__ void pw_tile(Grp& g, uint32_t b_hi, uint32_t b_lo, Loader&& load, Epi&& epi) {
-    pw_tile_c<KP, NP, KP>(g, b_hi, b_lo, static_cast<Loader&&>(load), static_cast<Epi&&>(epi));
+#pragma unroll
+    for (int k0 = 0; k0 < KP; k0 += 8) {
+        float a[8];
+        load(k0, a);
+        put_chunk<KP, NP>(g, a, k0 / 8, b_hi, b_lo);
+    }
+    get_tile<NP>(g, static_cast<Epi&&>(epi));
 }
 
-// CTA prologue shared by all kernels: TMEM allocation, barrier init, group context.
+// CTA prologue: TMEM allocation, barrier init.
 template <int G, int COLS>
-__device__ __forceinline__ Grp cta_setup(uint64_t* mbars, uint32_t* tmem_slot) {
+__device__ __forceinline__ Grp cta_setup(Pipe* pipes, uint32_t* tmem_slot) {
     static_assert(G * COLS <= kTmemCols, "TMEM columns");
     const int warp = threadIdx.x >> 5;
     if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
     if (threadIdx.x == 32) {
-        for (int i = 0; i < G; ++i) mbar_init(&mbars[i], 1);
+        for (int i = 0; i < G; ++i) {
+            mbar_init(&pipes[i].empty[0], 1); mbar_init(&pipes[i].empty[1], 1);
+            mbar_init(&pipes[i].dfull, 1);
+            pipes[i].arrivals[0] = 0; pipes[i].arrivals[1] = 0;
+        }
         fence_mbar_init();
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // weights written by this CTA -> visible to UMMA
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    const int grp = threadIdx.x >> 7;
     Grp g;
-    const int grp = warp >> 2;
     g.tcol = *tmem_slot + grp * COLS;
     g.tlane = g.tcol + ((uint32_t)(32 * (warp & 3)) << 16);
-    g.mbar = &mbars[grp];
-    g.parity = 0;
-    g.bar_id = 1 + grp;
+    g.pipe = &pipes[grp];
+    g.chunk = 0; g.dparity = 0;
     g.gtid = threadIdx.x & 127;
     return g;
 }
@@ -118,6 +153,10 @@ __device__ __forceinline__ void cta_teardown(uint32_t* tmem_slot) {
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, kTmemCols);
 }
+template <int G>
+__device__ __forceinline__ void producers_sync() { __syncthreads(); }
+// make weights written with ordinary stores visible to the tensor core's async proxy
+__device__ __forceinline__ void publish_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int count, int nthreads) {
     for (int i = threadIdx.x * 4; i < count; i += nthreads * 4)
@@ -166,27 +205,29 @@ struct PwArgs {
     int nout;               // real output channels
 };
 
-template <int KA, int KB, int SHA, int NP, int KC, int G, bool RELU>
-__global__ void __launch_bounds__(G * 128, 1)
+template <int KA, int KB, int SHA, int NP, int G, bool RELU>
+__global__ void __launch_bounds__(G * 128, 2)
 tc_pw_kernel(const __grid_constant__ PwArgs p) {
     constexpr int KP = KA + KB;
-    static_assert(KP % 8 == 0 && NP % 16 == 0, "shape");
-    constexpr int COLS = 2 * KC + NP;
+    constexpr int PF = 48;                                   // channels prefetched per batch of global loads
+    static_assert(KP % PF == 0 && NP % 16 == 0, "shape");
+    constexpr int COLS = kACols + NP;
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t mbars[G];
+    __shared__ __align__(8) Pipe pipes[G];
     __shared__ uint32_t tmem_slot;
     float* sB = smem;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     copy_f4(sB, p.wpack, WFL, G * 128);
-    Grp g = cta_setup<G, COLS>(mbars, &tmem_slot);
+    publish_smem();
+    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
-
     const int HW = p.out.H * p.out.W, W = p.out.W;
     const long long total = (long long)p.N * HW;
     const int ntiles = (int)((total + 127) / 128);
     const int grp = threadIdx.x >> 7;
+    const unsigned sCa = (unsigned)p.A.sC, sCb = (unsigned)p.B.sC, sCo = (unsigned)p.out.sC;
     for (int tile = blockIdx.x * G + grp; tile < ntiles; tile += gridDim.x * G) {
         const long long pos = (long long)tile * 128 + g.gtid;
         const bool valid = pos < total;
@@ -196,45 +237,45 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
         const float* baseA = p.A.base + (long long)n * p.A.sN + (long long)(y >> SHA) * p.A.W + (x >> SHA);
         const float* baseB = p.B.base + (long long)n * p.B.sN + px;
         float* obase = p.out.base + (long long)n * p.out.sN + px;
-        pw_tile_c<KP, NP, KC>(g, b_hi, b_lo,
-            [&](int k0, float (&a)[8]) {
+#pragma unroll 1
+        for (int kb = 0; kb < KP; kb += PF) {
+            float v[PF];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = k0 + j;
-                    float v = 0.f;
-                    if (valid) v = (k < KA) ? __ldg(baseA + (long long)p.ta.c[k] * p.A.sC) : __ldg(baseB + (long long)p.tb.c[k - KA] * p.B.sC);
-                    a[j] = v;
-                }
-            },
-            [&](int n0, float (&d)[16]) {
-                if (valid) {
+            for (int j = 0; j < PF; ++j) {
+                const int k = kb + j;
+                v[j] = 0.f;
+                if (valid) v[j] = (k < KA) ? __ldg(baseA + p.ta.c[k] * sCa) : __ldg(baseB + p.tb.c[KB ? k - KA : 0] * sCb);
+            }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int nn = n0 + j;
-                        if (nn < p.nout) {
-                            float v = fmaf(d[j], scale[nn], shift[nn]);
-                            if (RELU) v = fmaxf(v, 0.f);
-                            obase[(long long)p.tout.c[nn] * p.out.sC] = v;
-                        }
+            for (int c = 0; c < PF / 8; ++c) {
+                float a[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = v[c * 8 + j];
+                put_chunk<KP, NP>(g, a, kb / 8 + c, b_hi, b_lo);
+            }
+        }
+        get_tile<NP>(g, [&](int n0, float (&d)[16]) {
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int nn = n0 + j;
+                    if (nn < p.nout) {
+                        float r = fmaf(d[j], scale[nn], shift[nn]);
+                        if (RELU) r = fmaxf(r, 0.f);
+                        obase[p.tout.c[nn] * sCo] = r;
                     }
                 }
-            });
+            }
+        });
     }
     cta_teardown(&tmem_slot);
 }
 
 // ===================================================================================================
-// Band geometry shared by the DW-based kernels: a work item is (image, band of TR output rows).
-// The staged buffer holds rows [S*r0 - PAD, S*(r0+rows-1) + PAD] of the source planes with PAD zero columns
-// each side: staged row index rr <-> source row S*r0 - PAD + rr.
+// tc_dwpw_kernel: DW(KSxKS, stride S)+BN(+ReLU) -> PW(K->NP)+BN(+ReLU) -> planes, or (CHAIN) -> BN -> output conv
+// -> dense NCHW.  A work item is (image, band of TR output rows, branch); the band (+halo) of the K source planes
+// is staged in shared memory with zero padding.
 // ===================================================================================================
-template <int KS, int S>
-struct Band {
-    static constexpr int PAD = KS / 2;
-    __device__ static int staged_rows(int rows) { return S * (rows - 1) + KS; }
-};
-
-// DW(KSxKS, stride S)+BN(+ReLU) -> PW(KP->NP)+BN(+ReLU) -> store (optionally chained through a second PW).
 struct DwPwArgs {
     Planes in[2], out[2];      // per branch
     ChanTab tin[2], tout[2];
@@ -243,6 +284,7 @@ struct DwPwArgs {
     const float* wchain[2];    // chained output conv (tc pack, shift = bias), CHAIN only
     float* dstA[2]; float* dstB[2]; int split[2]; int M[2];   // CHAIN: dense NCHW destinations
     int N, TR, bandsPerImg, nbranch, nout;
+    int imgs;                  // images per work item (> 1 only when a band is a whole image)
 };
 
 template <int K, int NP, int G, int KS, int S, bool RELU_DW, bool RELU_OUT, bool CHAIN, int NP2>
@@ -250,11 +292,11 @@ __global__ void __launch_bounds__(G * 128, 1)
 tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     constexpr int KP = K;
     static_assert(KP % 8 == 0 && NP % 16 == 0, "shape");
-    constexpr int COLS = CHAIN ? (2 * KP + NP + ((2 * NP + NP2 > 2 * KP + NP) ? (2 * NP + NP2 - 2 * KP - NP) : 0)) : 2 * KP + NP;
+    constexpr int COLS = kACols + (CHAIN ? (NP > NP2 ? NP : NP2) : NP);
     constexpr int PAD = KS / 2;
     constexpr int DWR = KS == 3 ? 12 : 28;
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t mbars[G];
+    __shared__ __align__(8) Pipe pipes[G];
     __shared__ uint32_t tmem_slot;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     constexpr int WFL2 = CHAIN ? 2 * NP2 * NP + 2 * NP2 : 0;
@@ -262,43 +304,51 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     float* sB2 = sB + WFL;                     // chained pack
     float* sDW = sB2 + WFL2;                   // dw pack
     float* X = sDW + K * DWR;                  // staged planes
-
     const int Hout = p.out[0].H, Wout = p.out[0].W;
     const int Win = p.in[0].W;
     const int WS = Win + 2 * PAD;
-    const int RS = (S * (p.TR - 1) + KS) * WS;
-    Grp g = cta_setup<G, COLS>(mbars, &tmem_slot);
+    const int RS1 = (S * (p.TR - 1) + KS) * WS;           // one image's band of one plane
+    const int RS = RS1 * p.imgs;                           // plane stride of the staged buffer
+    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const uint32_t c_hi = smem_u32(sB2), c_lo = smem_u32(sB2 + NP2 * NP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
     const float* bias2 = sB2 + 2 * NP2 * NP + NP2;
+    const int ngroups = (p.N + p.imgs - 1) / p.imgs;       // image groups
+    const int items = ngroups * p.bandsPerImg * p.nbranch;
     const int grp = threadIdx.x >> 7;
-    const int items = p.N * p.bandsPerImg * p.nbranch;
     int loaded_branch = -1;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int br = item % p.nbranch;
         const int rem = item / p.nbranch;
-        const int n = rem / p.bandsPerImg;
-        const int r0 = (rem - n * p.bandsPerImg) * p.TR;
+        const int ig = rem / p.bandsPerImg;
+        const int r0 = (rem - ig * p.bandsPerImg) * p.TR;
         const int rows = min(p.TR, Hout - r0);
-        __syncthreads();                                   // previous item done with X / weights
+        const int n0img = ig * p.imgs;
+        const int nimg = min(p.imgs, p.N - n0img);
+        producers_sync<G>();                               // previous item done with X / weights
         if (br != loaded_branch) {
             copy_f4(sB, p.wpw[br], WFL, G * 128);
             if (CHAIN) copy_f4(sB2, p.wchain[br], WFL2, G * 128);
             copy_f4(sDW, p.wdw[br], K * DWR, G * 128);
             loaded_branch = br;
         }
-        stage_rows<K, PAD, G * 128>(X, RS, WS, p.in[br], p.tin[br], n, S * r0 - PAD, S * (rows - 1) + KS);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        const int npix = rows * Wout;
-        const int ntiles = (npix + 127) / 128;
-        for (int tile = grp; tile < ntiles; tile += G) {
+        for (int i = 0; i < nimg; ++i)
+            stage_rows<K, PAD, G * 128>(X + i * RS1, RS, WS, p.in[br], p.tin[br], n0img + i, S * r0 - PAD, S * (rows - 1) + KS);
+        publish_smem();
+        producers_sync<G>();
+        const int ppi = rows * Wout;                        // pixels per image in this band
+        const int npix = ppi * nimg;
+        const unsigned sCo = (unsigned)p.out[br].sC;
+        for (int tile = grp; tile * 128 < npix; tile += G) {
             const int q = tile * 128 + g.gtid;
             const bool valid = q < npix;
-            const int orow = valid ? q / Wout : 0, ox = valid ? q - orow * Wout : 0;
-            const float* win = X + (S * orow) * WS + S * ox;
+            const int im = valid ? q / ppi : 0;
+            const int qi = valid ? q - im * ppi : 0;
+            const int n = n0img + im;
+            const int orow = qi / Wout, ox = qi - orow * Wout;
+            const float* win = X + im * RS1 + (S * orow) * WS + S * ox;
             const long long opix = (long long)(r0 + orow) * Wout + ox;
             if (!CHAIN) {
                 float* obase = p.out[br].base + (long long)n * p.out[br].sN + opix;
@@ -312,45 +362,50 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
                                 if (nn < p.nout) {
                                     float v = fmaf(d[j], scale[nn], shift[nn]);
                                     if (RELU_OUT) v = fmaxf(v, 0.f);
-                                    obase[(long long)p.tout[br].c[nn] * p.out[br].sC] = v;
+                                    obase[p.tout[br].c[nn] * sCo] = v;
                                 }
                             }
                         }
                     });
             } else {
-                // features (NP columns, real p.nout) -> BN -> second UMMA against the output conv -> dense NCHW
-                // TMEM of the second contraction: A_hi [0,NP) A_lo [NP,2NP) D2 [2NP, 2NP+NP2) — it reuses the
-                // group's columns once the first D has been read back.
-                float f[NP];
-                pw_tile<KP, NP>(g, b_hi, b_lo,
-                    [&](int k0, float (&a)[8]) { dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a); },
-                    [&](int n0, float (&d)[16]) {
+                // features (NP columns, p.nout real) -> BN -> second contraction against the output conv -> dense NCHW.
+                // The feature tile goes straight back to TMEM as the A operand, 16 columns (two chunks) at a time.
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float v = fmaf(d[j], scale[n0 + j], shift[n0 + j]);
-                            if (RELU_OUT) v = fmaxf(v, 0.f);
-                            f[n0 + j] = valid ? v : 0.f;
-                        }
-                    });
+                for (int k0 = 0; k0 < KP; k0 += 8) {
+                    float a[8];
+                    dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a);
+                    put_chunk<KP, NP>(g, a, k0 / 8, b_hi, b_lo);
+                }
+                float f[NP];
+                get_tile<NP>(g, [&](int n0, float (&d)[16]) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v = fmaf(d[j], scale[n0 + j], shift[n0 + j]);
+                        if (RELU_OUT) v = fmaxf(v, 0.f);
+                        f[n0 + j] = valid ? v : 0.f;
+                    }
+                });
+#pragma unroll
+                for (int k0 = 0; k0 < NP; k0 += 8) {
+                    float a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = f[k0 + j];
+                    put_chunk<NP, NP2>(g, a, k0 / 8, c_hi, c_lo);
+                }
                 const int HW = Hout * Wout;
                 const int split = p.split[br], M = p.M[br];
                 float* dA = p.dstA[br]; float* dB = p.dstB[br];
-                pw_tile<NP, NP2>(g, c_hi, c_lo,
-                    [&](int k0, float (&a)[8]) {
+                get_tile<NP2>(g, [&](int n0, float (&d)[16]) {
+                    if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) a[j] = f[k0 + j];
-                    },
-                    [&](int n0, float (&d)[16]) {
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int m = n0 + j;
-                                const float v = d[j] + bias2[m];
-                                if (m < split) dA[((long long)n * split + m) * HW + opix] = v;
-                                else if (m < M) dB[((long long)n * (M - split) + (m - split)) * HW + opix] = v;
-                            }
+                        for (int j = 0; j < 16; ++j) {
+                            const int m = n0 + j;
+                            const float v = d[j] + bias2[m];
+                            if (m < split) dA[((long long)n * split + m) * HW + opix] = v;
+                            else if (m < M) dB[((long long)n * (M - split) + (m - split)) * HW + opix] = v;
                         }
-                    });
+                    }
+                });
             }
         }
     }
@@ -370,12 +425,12 @@ struct S1Args {
 };
 
 template <int K, int NP, int G>
-__global__ void __launch_bounds__(G * 128, 1)
+__global__ void __launch_bounds__(G * 128, 2)
 tc_s1_kernel(const __grid_constant__ S1Args p) {
     constexpr int KP = K;
-    constexpr int COLS = 2 * KP + NP;
+    constexpr int COLS = kACols + NP;
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t mbars[G];
+    __shared__ __align__(8) Pipe pipes[G];
     __shared__ uint32_t tmem_slot;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     float* sB1 = smem;
@@ -387,21 +442,23 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
     copy_f4(sB1, p.w1, WFL, G * 128);
     copy_f4(sB2, p.w2, WFL, G * 128);
     copy_f4(sDW, p.wdw, K * 12, G * 128);
-    Grp g = cta_setup<G, COLS>(mbars, &tmem_slot);
+    publish_smem();
+    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
     const uint32_t b2_hi = smem_u32(sB2), b2_lo = smem_u32(sB2 + NP * KP);
     const float* sc1 = sB1 + 2 * NP * KP; const float* sh1 = sc1 + NP;
     const float* sc2 = sB2 + 2 * NP * KP; const float* sh2 = sc2 + NP;
-    const int grp = threadIdx.x >> 7;
     const int items = p.N * p.bandsPerImg;
+    const int grp = threadIdx.x >> 7;
+    const unsigned sC = (unsigned)p.P.sC;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int n = item / p.bandsPerImg;
         const int r0 = (item - n * p.bandsPerImg) * p.TR;
         const int rows = min(p.TR, H - r0);
-        __syncthreads();
+        producers_sync<G>();
         // zero the band buffer: padding columns / out-of-image rows must read as 0 for the depthwise
         for (int i = threadIdx.x * 4; i < K * RS; i += G * 128 * 4) *reinterpret_cast<float4*>(T + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
+        producers_sync<G>();
         // ---- phase B: pw1 + BN + ReLU on every in-image pixel of rows [r0-1, r0+rows] -> T --------------------------
         const int gr_lo = max(r0 - 1, 0), gr_hi = min(r0 + rows, H - 1);
         const int npos = (gr_hi - gr_lo + 1) * W;
@@ -412,10 +469,13 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
             const int gr = gr_lo + rr;
             const float* ibase = p.P.base + (long long)n * p.P.sN + (long long)gr * W + x;
             float* tpos = T + (gr - (r0 - 1)) * WS + 1 + x;
+            float v[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) v[k] = valid ? __ldg(ibase + p.tin.c[k] * sC) : 0.f;    // all loads in flight at once
             pw_tile<KP, NP>(g, b1_hi, b1_lo,
                 [&](int k0, float (&a)[8]) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = valid ? __ldg(ibase + (long long)p.tin.c[k0 + j] * p.P.sC) : 0.f;
+                    for (int j = 0; j < 8; ++j) a[j] = v[k0 + j];
                 },
                 [&](int n0, float (&d)[16]) {
                     if (valid) {
@@ -425,7 +485,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
                     }
                 });
         }
-        __syncthreads();
+        producers_sync<G>();
         // ---- phase C: dw3x3 + BN -> pw2 + BN + ReLU -> output planes -------------------------------------------
         const int npix = rows * W;
         for (int tile = grp; tile * 128 < npix; tile += G) {
@@ -440,7 +500,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (n0 + j < K) obase[(long long)p.tout.c[n0 + j] * p.P.sC] = fmaxf(fmaf(d[j], sc2[n0 + j], sh2[n0 + j]), 0.f);
+                            if (n0 + j < K) obase[p.tout.c[n0 + j] * sC] = fmaxf(fmaf(d[j], sc2[n0 + j], sh2[n0 + j]), 0.f);
                     }
                 });
         }
@@ -460,12 +520,12 @@ struct S2Args {
 };
 
 template <int K, int NP, int G>
-__global__ void __launch_bounds__(G * 128, 1)
+__global__ void __launch_bounds__(G * 128, 2)
 tc_s2_kernel(const __grid_constant__ S2Args p) {
     constexpr int KP = K;
-    constexpr int COLS = 2 * KP + NP;
+    constexpr int COLS = kACols + NP;
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) uint64_t mbars[G];
+    __shared__ __align__(8) Pipe pipes[G];
     __shared__ uint32_t tmem_slot;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     float* sBp = smem;
@@ -482,23 +542,25 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
     copy_f4(sB2, p.w2, WFL, G * 128);
     copy_f4(sDWp, p.wdwp, K * 12, G * 128);
     copy_f4(sDWm, p.wdwm, K * 12, G * 128);
-    Grp g = cta_setup<G, COLS>(mbars, &tmem_slot);
+    publish_smem();
+    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t bp_hi = smem_u32(sBp), bp_lo = smem_u32(sBp + NP * KP);
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
     const uint32_t b2_hi = smem_u32(sB2), b2_lo = smem_u32(sB2 + NP * KP);
     const float* scp = sBp + 2 * NP * KP; const float* shp = scp + NP;
     const float* sc1 = sB1 + 2 * NP * KP; const float* sh1 = sc1 + NP;
     const float* sc2 = sB2 + 2 * NP * KP; const float* sh2 = sc2 + NP;
-    const int grp = threadIdx.x >> 7;
     const int items = p.N * p.bandsPerImg;
+    const int grp = threadIdx.x >> 7;
+    const unsigned sCo = (unsigned)p.out.sC;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int n = item / p.bandsPerImg;
         const int r0 = (item - n * p.bandsPerImg) * p.TR;
         const int rows = min(p.TR, Hout - r0);
         const int gr0 = 2 * r0 - 1, nrows = 2 * rows + 1;
-        __syncthreads();
+        producers_sync<G>();
         stage_rows<K, 1, G * 128>(X, RS, WS, p.in, p.tin, n, gr0, nrows);
-        __syncthreads();
+        producers_sync<G>();
         const int npix = rows * Wout;
         // ---- proj: dw3x3 s2 + BN -> pw + BN + ReLU on the raw input ---------------------------------------------
         for (int tile = grp; tile * 128 < npix; tile += G) {
@@ -513,11 +575,11 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (n0 + j < K) obase[(long long)p.tout.c[n0 + j] * p.out.sC] = fmaxf(fmaf(d[j], scp[n0 + j], shp[n0 + j]), 0.f);
+                            if (n0 + j < K) obase[p.tout.c[n0 + j] * sCo] = fmaxf(fmaf(d[j], scp[n0 + j], shp[n0 + j]), 0.f);
                     }
                 });
         }
-        __syncthreads();
+        producers_sync<G>();
         // ---- main pw1 in place on every staged in-image pixel ------------------------------------------------------
         const int gr_lo = max(gr0, 0), gr_hi = min(gr0 + nrows - 1, Hin - 1);
         const int npos = (gr_hi - gr_lo + 1) * Win;
@@ -539,7 +601,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
                     }
                 });
         }
-        __syncthreads();
+        producers_sync<G>();
         // ---- main: dw3x3 s2 + BN -> pw2 + BN + ReLU ---------------------------------------------------------------
         for (int tile = grp; tile * 128 < npix; tile += G) {
             const int q = tile * 128 + g.gtid;
@@ -553,7 +615,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
                     if (valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (n0 + j < K) obase[(long long)p.tout.c[K + n0 + j] * p.out.sC] = fmaxf(fmaf(d[j], sc2[n0 + j], sh2[n0 + j]), 0.f);
+                            if (n0 + j < K) obase[p.tout.c[K + n0 + j] * sCo] = fmaxf(fmaf(d[j], sc2[n0 + j], sh2[n0 + j]), 0.f);
                     }
                 });
         }
@@ -583,11 +645,11 @@ int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout
         const size_t wfl = (size_t)2 * (2 * NP * KK + 2 * NP) + KK * 12;
         auto bytes = [&](int tr) { return (wfl + (size_t)KK * (tr + 2) * (W + 2) + 4) * sizeof(float); };
         int TR = H;
-        while (TR > 1 && bytes(TR) > 200 * 1024) TR = (TR + 1) / 2;
+        while (TR > 1 && bytes(TR) > 110 * 1024) TR = (TR + 1) / 2;     // two CTAs per SM
         a.TR = TR; a.bandsPerImg = (H + TR - 1) / TR;
         TRYL(set_smem_attr(kern, bytes(TR)));
         const int items = N * a.bandsPerImg;
-        kern<<<min(items, sm_count()), G * 128, bytes(TR), s>>>(a);
+        kern<<<min(items, 2 * sm_count()), G * 128, bytes(TR), s>>>(a);
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
@@ -605,11 +667,11 @@ int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin,
         const size_t wfl = (size_t)3 * (2 * NP * KK + 2 * NP) + 2 * KK * 12;
         auto bytes = [&](int tr) { return (wfl + (size_t)KK * (2 * tr + 1) * (Win + 2) + 4) * sizeof(float); };
         int TR = Hout;
-        while (TR > 1 && bytes(TR) > 200 * 1024) --TR;
+        while (TR > 1 && bytes(TR) > 110 * 1024) --TR;
         a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR;
         TRYL(set_smem_attr(kern, bytes(TR)));
         const int items = N * a.bandsPerImg;
-        kern<<<min(items, sm_count()), G * 128, bytes(TR), s>>>(a);
+        kern<<<min(items, 2 * sm_count()), G * 128, bytes(TR), s>>>(a);
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
@@ -629,15 +691,30 @@ int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, 
         a.nout = nout;
         const size_t bytes = (size_t)(2 * NP * KP + 2 * NP) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
-        kern<<<min((ntiles + G - 1) / G, sm_count()), G * 128, bytes, s>>>(a);
+        const int per_sm = bytes <= 110 * 1024 ? 2 : 1;
+        kern<<<min((ntiles + G - 1) / G, per_sm * sm_count()), G * 128, bytes, s>>>(a);
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (kind == 0) return run(tc_pw_kernel<96, 0, 0, 96, 96, 1, true>, 96, 96, 1, 96);
-    if (kind == 1) return run(tc_pw_kernel<192, 0, 0, 80, 96, 1, true>, 192, 80, 1, 72);
-    if (kind == 2) return run(tc_pw_kernel<192, 96, 1, 80, 96, 1, true>, 288, 80, 1, 72);
+    if (kind == 0) return run(tc_pw_kernel<96, 0, 0, 96, 2, true>, 96, 96, 2, 96);
+    if (kind == 1) return run(tc_pw_kernel<192, 0, 0, 80, 2, true>, 192, 80, 2, 72);
+    if (kind == 2) return run(tc_pw_kernel<192, 96, 1, 80, 2, true>, 288, 80, 2, 72);
     set_error("tc_launch_pw: unknown kind %d", kind);
     return YFV2_EUNSUPPORTED;
+}
+
+// Band height / images per item for the DW->PW kernels: whole images (several per item) when one fits comfortably,
+// otherwise row bands of one image.
+static void dwpw_geometry(DwPwArgs& a, int Hout, size_t wfl_floats, size_t plane_floats_per_row, int halo_rows, int S, int Wout, int G) {
+    const size_t cap = 200 * 1024 / sizeof(float);
+    auto band_floats = [&](int tr) { return plane_floats_per_row * (size_t)(S * (tr - 1) + halo_rows); };
+    int TR = Hout;
+    while (TR > 1 && wfl_floats + band_floats(TR) > cap) --TR;
+    a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR; a.imgs = 1;
+    if (a.bandsPerImg == 1) {
+        const int tiles1 = (Hout * Wout + 127) / 128;                 // tiles one image needs
+        while (a.imgs * tiles1 < G && wfl_floats + band_floats(TR) * (a.imgs + 1) <= cap) ++a.imgs;
+    }
 }
 
 // K=96 DW3x3(stride)->PW (+ReLU) for nbranch branches (stage-4 blocks)
@@ -647,20 +724,19 @@ int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* t
     for (int b = 0; b < nbranch; ++b) { a.in[b] = in[b]; a.out[b] = out[b]; a.tin[b] = tin[b]; a.tout[b] = tout[b]; a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
     a.N = N; a.nbranch = nbranch; a.nout = 96;
     const int Hout = out[0].H, Win = in[0].W;
+    constexpr int G = 2;
     auto run = [&](auto kern, int S) -> int {
         const size_t wfl = (size_t)(2 * 96 * 96 + 2 * 96) + 96 * 12;
-        auto bytes = [&](int tr) { return (wfl + (size_t)96 * (S * (tr - 1) + 3) * (Win + 2) + 4) * sizeof(float); };
-        int TR = Hout;
-        while (TR > 1 && bytes(TR) > 200 * 1024) --TR;
-        a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR;
-        TRYL(set_smem_attr(kern, bytes(TR)));
-        const int items = N * a.bandsPerImg * nbranch;
-        kern<<<min(items, sm_count()), 128, bytes(TR), s>>>(a);
+        dwpw_geometry(a, Hout, wfl + 4, (size_t)96 * (Win + 2), 3, S, out[0].W, G);
+        const size_t bytes = (wfl + (size_t)96 * (S * (a.TR - 1) + 3) * (Win + 2) * a.imgs + 4) * sizeof(float);
+        TRYL(set_smem_attr(kern, bytes));
+        const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * nbranch;
+        kern<<<min(items, sm_count()), G * 128, bytes, s>>>(a);
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (stride == 1) return run(tc_dwpw_kernel<96, 96, 1, 3, 1, false, true, false, 16>, 1);
-    return run(tc_dwpw_kernel<96, 96, 1, 3, 2, false, true, false, 16>, 2);
+    if (stride == 1) return run(tc_dwpw_kernel<96, 96, G, 3, 1, false, true, false, 16>, 1);
+    return run(tc_dwpw_kernel<96, 96, G, 3, 2, false, true, false, 16>, 2);
 }
 
 // heads: half 0: T = BN(pw(ReLU(BN(dw5x5(S)))));  half 1: preds = outconv(BN(pw(ReLU(BN(dw5x5(T)))))) + bias.
@@ -680,22 +756,20 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
     }
     const int Hout = sIn.H, Win = sIn.W;
-    constexpr int NP = 80, NP2 = 96;
+    constexpr int NP = 80, NP2 = 96, G = 2;
     if (A + C > NP2 || 4 * A > NP2) { set_error("tc heads: A+C=%d exceeds the chained tile (%d)", A + C, NP2); return YFV2_EUNSUPPORTED; }
     auto run = [&](auto kern, bool chain) -> int {
         const size_t wfl = (size_t)(2 * NP * 72 + 2 * NP) + (chain ? (size_t)(2 * NP2 * NP + 2 * NP2) : 0) + 72 * 28;
-        auto bytes = [&](int tr) { return (wfl + (size_t)72 * (tr + 4) * (Win + 4) + 4) * sizeof(float); };
-        int TR = Hout;
-        while (TR > 1 && bytes(TR) > 200 * 1024) --TR;
-        a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR;
-        TRYL(set_smem_attr(kern, bytes(TR)));
-        const int items = N * a.bandsPerImg * 2;
-        kern<<<min(items, sm_count()), 2 * 128, bytes(TR), s>>>(a);
+        dwpw_geometry(a, Hout, wfl + 4, (size_t)72 * (Win + 4), 5, 1, sIn.W, G);
+        const size_t bytes = (wfl + (size_t)72 * (a.TR + 4) * (Win + 4) * a.imgs + 4) * sizeof(float);
+        TRYL(set_smem_attr(kern, bytes));
+        const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * 2;
+        kern<<<min(items, sm_count()), G * 128, bytes, s>>>(a);
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (half == 0) return run(tc_dwpw_kernel<72, NP, 2, 5, 1, true, false, false, 16>, false);
-    return run(tc_dwpw_kernel<72, NP, 2, 5, 1, true, false, true, NP2>, true);
+    if (half == 0) return run(tc_dwpw_kernel<72, NP, G, 5, 1, true, false, false, 16>, false);
+    return run(tc_dwpw_kernel<72, NP, G, 5, 1, true, false, true, NP2>, true);
 }
 
 }  // namespace yfv2
