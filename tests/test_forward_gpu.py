@@ -134,15 +134,3 @@ def test_every_fused_stage_against_reference_taps(golden_dir):
     np.testing.assert_allclose(plan.debug_gather(17).cpu().numpy(), g["tap_S2"], **TOL)
     for i, p in enumerate(preds):
         np.testing.assert_allclose(p.cpu().numpy(), g["pred%d" % i], **TOL)
-
-
-def test_ffma_engine_still_matches(golden_dir, monkeypatch):
-    """The FFMA kernels stay available (YFV2_ENGINE=ffma at plan creation) as the cross-check of the tcgen05 path."""
-    monkeypatch.setenv("YFV2_ENGINE", "ffma")
-    g = dict(np.load(os.path.join(golden_dir, "net_352.npz")))
-    m = make_model(synth.make_state_dict(21))
-    preds = m(synth.make_images(22, 1, 352, 352).cuda())
-    plan = next(iter(m._plans.values()))
-    assert "stage4.1" in plan.stage_names and "stage4.1/pw1" not in plan.stage_names
-    for i, p in enumerate(preds):
-        np.testing.assert_allclose(p.cpu().numpy(), g["pred%d" % i], err_msg="pred%d" % i, **TOL)

@@ -1,7 +1,11 @@
 // Shared declarations for libyfv2.so (sm_100a only).
 //
 // Activation storage ("plane pools"): every intermediate tensor of the network lives as separate
-// channel planes, plane(n, c) = base + n*sN + c*sC, each plane a dense H*W fp32 image.  A logical
+// channel planes, plane(n, c) = base + n*sN + c*sC.  A plane is an H x W fp32 image inside a ZERO FRAME:
+// rows of Ws floats (Ws = W + 2*pad rounded up to 4), `pad` zero rows above and below, pixel (y,x) at
+// org + y*Ws + x.  Kernels only ever write interior pixels, so the frame (zeroed once per workspace) is
+// the zero padding of every 3x3 / 5x5 convolution and a band of rows *with its halo* is one contiguous,
+// 16-byte aligned run: it is staged into shared memory by a single TMA bulk copy per plane.  A logical
 // tensor is a list of physical plane ids (ChanTab).  ShuffleNetV2's channel_shuffle / split / concat
 // (reference model/backbone/shufflenetv2.py:48-63) therefore cost nothing: they are edits of the id
 // list done on the host when the plan is built, and the "passthrough" half of a stride-1 block is
@@ -22,7 +26,10 @@ struct Planes {
     float* base;
     long long sN;   // floats between consecutive images
     long long sC;   // floats between consecutive planes
-    int H, W;
+    int H, W;       // image size
+    int Ws;         // row stride (floats), multiple of 4
+    int pad;        // zero frame width (rows and columns)
+    int org;        // offset of pixel (0,0) inside a plane = pad*Ws + pad
 };
 
 struct ChanTab {
@@ -96,31 +103,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Stage rows [gr0, gr0+nrows) of the K planes listed in tab into X[k][rr*WS + PAD + x]; WS = W + 2*PAD.
-// Out-of-image rows and the PAD columns are written as zeros (the zero padding of the next conv).
-template <int K, int PAD, int NTHREADS>
-__device__ __forceinline__ void stage_rows(float* __restrict__ X, int RS, int WS, const Planes& P, const ChanTab& tab,
-                                           int n, int gr0, int nrows) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = NTHREADS >> 5;
-    const int W = P.W, H = P.H;
-    for (int row = warp; row < K * nrows; row += nwarps) {
-        const int k = row / nrows, rr = row - k * nrows;
-        const int gr = gr0 + rr;
-        float* dst = X + k * RS + rr * WS;
-        if (gr >= 0 && gr < H) {
-            const float* src = plane_ptr(P, n, tab.c[k]) + (long long)gr * W;
-            for (int cc = lane; cc < WS; cc += 32) {
-                const int x = cc - PAD;
-                if (x >= 0 && x < W) cp_async4(dst + cc, src + x);      // many loads in flight per warp
-                else dst[cc] = 0.f;
-            }
-        } else {
-            for (int cc = lane; cc < WS; cc += 32) dst[cc] = 0.f;
-        }
-    }
-    cp_async_wait_all();      // the caller's __syncthreads() publishes the tile
-}
-
 int sm_count();
 constexpr size_t kSmemCap = 227 * 1024;
 
@@ -133,40 +115,5 @@ struct StemArgs {
     const float* wpack;  // STEM layout
 };
 int launch_stem(const StemArgs& a, cudaStream_t s);
-
-struct ShuffleArgs {
-    int K;               // branch width: 24 / 48 / 96
-    int stride;          // 1 or 2
-    int N;
-    Planes in, out;      // stride 1: same pool
-    ChanTab tin;         // stride 1: K main-branch inputs (odd logical channels); stride 2: K inputs
-    ChanTab tout;        // stride 1: K output planes; stride 2: 2K (proj then main)
-    const float* wpack;  // see k_shuffle.cu
-};
-int launch_shuffle(const ShuffleArgs& a, cudaStream_t s);
-size_t shuffle_pack_floats(int K, int stride);
-
-struct FpnArgs {
-    int N;
-    Planes c3;  ChanTab t3;   // 192 planes at H/32
-    Planes c2;  ChanTab t2;   // 96 planes at H/16
-    Planes s3, s2;            // outputs: 72 planes each (ids 0..71)
-    const float* w3;          // PW 192->72
-    const float* w2;          // PW 288->72  (k order: up(C3) 0..191, C2 192..287; fpn.py:58)
-};
-int launch_fpn(const FpnArgs& a, int which /*0: S3, 1: S2*/, cudaStream_t s);
-
-struct HeadArgs {
-    int N, A, C;
-    Planes s;                 // input 72 planes (S2 or S3)
-    Planes t_cls, t_reg;      // scratch 72 planes each (mid-block activations)
-    const float* w_cls;       // DWConvblock pack (see k_head.cu) for the cls head
-    const float* w_reg;
-    const float* w_out_reg;   // PW 72->4A with bias as shift, scale 1
-    const float* w_out_oc;    // PW 72->(A+C): obj rows first, then cls rows
-    float* reg; float* obj; float* cls;   // dense NCHW outputs for this level
-};
-int launch_heads(const HeadArgs& a, int half /*0: first dw+pw, 1: second dw+pw + output convs*/, cudaStream_t s);
-size_t head_pack_floats();
 
 }  // namespace yfv2

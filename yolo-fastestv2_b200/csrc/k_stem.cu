@@ -125,7 +125,7 @@ stem_kernel(const void* __restrict__ xin, Planes out, const float* __restrict__ 
                 m = fmaxf(m, cv[1]); m = fmaxf(m, cv[2]);
                 m = fmaxf(m, cv[CT_W]); m = fmaxf(m, cv[CT_W + 1]); m = fmaxf(m, cv[CT_W + 2]);
                 m = fmaxf(m, cv[2 * CT_W]); m = fmaxf(m, cv[2 * CT_W + 1]); m = fmaxf(m, cv[2 * CT_W + 2]);
-                plane_ptr(out, n, g * CG + j)[oy * WO + ox] = m;
+                plane_ptr(out, n, g * CG + j)[out.org + oy * out.Ws + ox] = m;
             }
         }
         __syncthreads();

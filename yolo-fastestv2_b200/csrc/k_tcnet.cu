@@ -13,6 +13,10 @@
 //   tc_dwpw_kernel  out = act(BN(pw( act(BN(dw(in))) )))        (+ optional chained output conv; heads, K=96 blocks)
 //   tc_s1_kernel    ShuffleV2 stride-1 block, fully fused       (pw1 -> smem -> dw3x3 -> pw2)
 //   tc_s2_kernel    ShuffleV2 stride-2 block, fully fused       (proj: dw s2 -> pw;  main: pw1 -> smem -> dw s2 -> pw2)
+//
+// Staging: planes live in global memory inside zero frames (common.cuh), so the rows a band needs, halo and
+// padding included, are one contiguous 16-byte-aligned run per plane: one TMA bulk copy (cp.async.bulk, UBLKCP)
+// per plane, issued by K different threads, completion counted on an mbarrier.  No per-element address math.
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -158,6 +162,18 @@ __device__ __forceinline__ void producers_sync() { __syncthreads(); }
 // make weights written with ordinary stores visible to the tensor core's async proxy
 __device__ __forceinline__ void publish_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Stage `nrows` frame rows starting at frame row fr0 of the K planes in `tab` (image n) into X[k][.] (plane stride RS
+// floats).  One bulk copy per plane.  Callers: all threads; wait with mbar_wait(bar, parity) afterwards.
+template <int K>
+__device__ __forceinline__ void stage_bulk(float* X, int RS, const Planes& P, const ChanTab& tab, int n, int fr0, int nrows, uint64_t* bar,
+                                           int tid0) {
+    const int t = (int)threadIdx.x - tid0;
+    if (t >= 0 && t < K) {
+        const float* src = plane_ptr(P, n, tab.c[t]) + (long long)fr0 * P.Ws;
+        bulk_g2s(X + (size_t)t * RS, src, (uint32_t)(nrows * P.Ws * sizeof(float)), bar);
+    }
+}
+
 __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ src, int count, int nthreads) {
     for (int i = threadIdx.x * 4; i < count; i += nthreads * 4)
         *reinterpret_cast<float4*>(dst + i) = __ldg(reinterpret_cast<const float4*>(src + i));
@@ -194,7 +210,7 @@ __device__ __forceinline__ void dw8(const float* __restrict__ win, int RS, int W
 
 // ===================================================================================================
 // tc_pw_kernel: pointwise over planes.  KA channels read through (y>>SHA, x>>SHA) from A, then KB channels
-// at (y,x) from B (K = KA+KB must be a multiple of 8).  One tile = 128 consecutive pixels of the flattened
+// at (y,x) from B (K = KA+KB must be a multiple of 48).  One tile = 128 consecutive pixels of the flattened
 // (image, pixel) index space.
 // ===================================================================================================
 struct PwArgs {
@@ -234,9 +250,9 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
         const int n = valid ? (int)(pos / HW) : 0;
         const int px = valid ? (int)(pos - (long long)n * HW) : 0;
         const int y = px / W, x = px - y * W;
-        const float* baseA = p.A.base + (long long)n * p.A.sN + (long long)(y >> SHA) * p.A.W + (x >> SHA);
-        const float* baseB = p.B.base + (long long)n * p.B.sN + px;
-        float* obase = p.out.base + (long long)n * p.out.sN + px;
+        const float* baseA = p.A.base + (long long)n * p.A.sN + p.A.org + (y >> SHA) * p.A.Ws + (x >> SHA);
+        const float* baseB = p.B.base + (long long)n * p.B.sN + p.B.org + y * p.B.Ws + x;
+        float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + y * p.out.Ws + x;
 #pragma unroll 1
         for (int kb = 0; kb < KP; kb += PF) {
             float v[PF];
@@ -273,8 +289,8 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
 
 // ===================================================================================================
 // tc_dwpw_kernel: DW(KSxKS, stride S)+BN(+ReLU) -> PW(K->NP)+BN(+ReLU) -> planes, or (CHAIN) -> BN -> output conv
-// -> dense NCHW.  A work item is (image, band of TR output rows, branch); the band (+halo) of the K source planes
-// is staged in shared memory with zero padding.
+// -> dense NCHW.  A work item is (image group, band of TR output rows, branch); the band (+halo) of the K source
+// planes of each image is staged in shared memory by bulk copies.
 // ===================================================================================================
 struct DwPwArgs {
     Planes in[2], out[2];      // per branch
@@ -291,12 +307,13 @@ template <int K, int NP, int G, int KS, int S, bool RELU_DW, bool RELU_OUT, bool
 __global__ void __launch_bounds__(G * 128, 1)
 tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     constexpr int KP = K;
-    static_assert(KP % 8 == 0 && NP % 16 == 0, "shape");
+    static_assert(KP % 8 == 0 && NP % 16 == 0 && K <= G * 128, "shape");
     constexpr int COLS = kACols + (CHAIN ? (NP > NP2 ? NP : NP2) : NP);
-    constexpr int PAD = KS / 2;
+    constexpr int PADK = KS / 2;
     constexpr int DWR = KS == 3 ? 12 : 28;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
+    __shared__ __align__(8) uint64_t xbar;
     __shared__ uint32_t tmem_slot;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     constexpr int WFL2 = CHAIN ? 2 * NP2 * NP + 2 * NP2 : 0;
@@ -305,10 +322,11 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     float* sDW = sB2 + WFL2;                   // dw pack
     float* X = sDW + K * DWR;                  // staged planes
     const int Hout = p.out[0].H, Wout = p.out[0].W;
-    const int Win = p.in[0].W;
-    const int WS = Win + 2 * PAD;
+    const int WS = p.in[0].Ws;
     const int RS1 = (S * (p.TR - 1) + KS) * WS;           // one image's band of one plane
     const int RS = RS1 * p.imgs;                           // plane stride of the staged buffer
+    const int coff = p.in[0].pad - PADK;                   // frame column of the window's left edge for ox = 0
+    if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const uint32_t c_hi = smem_u32(sB2), c_lo = smem_u32(sB2 + NP2 * NP);
@@ -319,6 +337,7 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     const int items = ngroups * p.bandsPerImg * p.nbranch;
     const int grp = threadIdx.x >> 7;
     int loaded_branch = -1;
+    uint32_t xparity = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int br = item % p.nbranch;
         const int rem = item / p.nbranch;
@@ -327,17 +346,22 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
         const int rows = min(p.TR, Hout - r0);
         const int n0img = ig * p.imgs;
         const int nimg = min(p.imgs, p.N - n0img);
-        producers_sync<G>();                               // previous item done with X / weights
+        const int nrows = S * (rows - 1) + KS;
+        __syncthreads();                                   // previous item done with X / weights
+        publish_smem();                                    // order those generic reads before the async-proxy writes below
+        if (threadIdx.x == 0) mbar_expect_tx(&xbar, (uint32_t)(K * nimg * nrows * WS * sizeof(float)));
+        for (int i = 0; i < nimg; ++i)
+            stage_bulk<K>(X + i * RS1, RS, p.in[br], p.tin[br], n0img + i, S * r0 + p.in[br].pad - PADK, nrows, &xbar, 0);
         if (br != loaded_branch) {
             copy_f4(sB, p.wpw[br], WFL, G * 128);
             if (CHAIN) copy_f4(sB2, p.wchain[br], WFL2, G * 128);
             copy_f4(sDW, p.wdw[br], K * DWR, G * 128);
             loaded_branch = br;
+            publish_smem();
         }
-        for (int i = 0; i < nimg; ++i)
-            stage_rows<K, PAD, G * 128>(X + i * RS1, RS, WS, p.in[br], p.tin[br], n0img + i, S * r0 - PAD, S * (rows - 1) + KS);
-        publish_smem();
-        producers_sync<G>();
+        __syncthreads();
+        mbar_wait(&xbar, xparity);
+        xparity ^= 1u;
         const int ppi = rows * Wout;                        // pixels per image in this band
         const int npix = ppi * nimg;
         const unsigned sCo = (unsigned)p.out[br].sC;
@@ -348,10 +372,9 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
             const int qi = valid ? q - im * ppi : 0;
             const int n = n0img + im;
             const int orow = qi / Wout, ox = qi - orow * Wout;
-            const float* win = X + im * RS1 + (S * orow) * WS + S * ox;
-            const long long opix = (long long)(r0 + orow) * Wout + ox;
+            const float* win = X + im * RS1 + (S * orow) * WS + S * ox + coff;
             if (!CHAIN) {
-                float* obase = p.out[br].base + (long long)n * p.out[br].sN + opix;
+                float* obase = p.out[br].base + (long long)n * p.out[br].sN + p.out[br].org + (r0 + orow) * p.out[br].Ws + ox;
                 pw_tile<KP, NP>(g, b_hi, b_lo,
                     [&](int k0, float (&a)[8]) { dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a); },
                     [&](int n0, float (&d)[16]) {
@@ -369,7 +392,6 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
                     });
             } else {
                 // features (NP columns, p.nout real) -> BN -> second contraction against the output conv -> dense NCHW.
-                // The feature tile goes straight back to TMEM as the A operand, 16 columns (two chunks) at a time.
 #pragma unroll
                 for (int k0 = 0; k0 < KP; k0 += 8) {
                     float a[8];
@@ -393,6 +415,7 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
                     put_chunk<NP, NP2>(g, a, k0 / 8, c_hi, c_lo);
                 }
                 const int HW = Hout * Wout;
+                const long long opix = (long long)(r0 + orow) * Wout + ox;
                 const int split = p.split[br], M = p.M[br];
                 float* dA = p.dstA[br]; float* dB = p.dstB[br];
                 get_tile<NP2>(g, [&](int n0, float (&d)[16]) {
@@ -455,10 +478,15 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
         const int n = item / p.bandsPerImg;
         const int r0 = (item - n * p.bandsPerImg) * p.TR;
         const int rows = min(p.TR, H - r0);
-        producers_sync<G>();
-        // zero the band buffer: padding columns / out-of-image rows must read as 0 for the depthwise
-        for (int i = threadIdx.x * 4; i < K * RS; i += G * 128 * 4) *reinterpret_cast<float4*>(T + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-        producers_sync<G>();
+        __syncthreads();
+        // only the padding of T needs zeros: the two pad columns of every row and whole out-of-image halo rows
+        for (int i = threadIdx.x; i < K * (rows + 2); i += G * 128) {
+            const int k = i / (rows + 2), rr = i - k * (rows + 2);
+            const int gr = r0 - 1 + rr;
+            float* row = T + k * RS + rr * WS;
+            if (gr < 0 || gr >= H) { for (int c = 0; c < WS; ++c) row[c] = 0.f; }
+            else { row[0] = 0.f; row[W + 1] = 0.f; }
+        }
         // ---- phase B: pw1 + BN + ReLU on every in-image pixel of rows [r0-1, r0+rows] -> T --------------------------
         const int gr_lo = max(r0 - 1, 0), gr_hi = min(r0 + rows, H - 1);
         const int npos = (gr_hi - gr_lo + 1) * W;
@@ -467,7 +495,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
             const bool valid = q < npos;
             const int rr = valid ? q / W : 0, x = valid ? q - rr * W : 0;
             const int gr = gr_lo + rr;
-            const float* ibase = p.P.base + (long long)n * p.P.sN + (long long)gr * W + x;
+            const float* ibase = p.P.base + (long long)n * p.P.sN + p.P.org + gr * p.P.Ws + x;
             float* tpos = T + (gr - (r0 - 1)) * WS + 1 + x;
             float v[KP];
 #pragma unroll
@@ -485,7 +513,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
                     }
                 });
         }
-        producers_sync<G>();
+        __syncthreads();
         // ---- phase C: dw3x3 + BN -> pw2 + BN + ReLU -> output planes -------------------------------------------
         const int npix = rows * W;
         for (int tile = grp; tile * 128 < npix; tile += G) {
@@ -493,7 +521,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
             const bool valid = q < npix;
             const int orow = valid ? q / W : 0, ox = valid ? q - orow * W : 0;
             const float* win = T + orow * WS + ox;
-            float* obase = p.P.base + (long long)n * p.P.sN + (long long)(r0 + orow) * W + ox;
+            float* obase = p.P.base + (long long)n * p.P.sN + p.P.org + (r0 + orow) * p.P.Ws + ox;
             pw_tile<KP, NP>(g, b2_hi, b2_lo,
                 [&](int k0, float (&a)[8]) { dw8<3, 1, false>(win, RS, WS, sDW, k0, valid, a); },
                 [&](int n0, float (&d)[16]) {
@@ -524,8 +552,10 @@ __global__ void __launch_bounds__(G * 128, 2)
 tc_s2_kernel(const __grid_constant__ S2Args p) {
     constexpr int KP = K;
     constexpr int COLS = kACols + NP;
+    static_assert(K <= G * 128, "one bulk copy per thread");
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
+    __shared__ __align__(8) uint64_t xbar;
     __shared__ uint32_t tmem_slot;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     float* sBp = smem;
@@ -534,15 +564,17 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
     float* sDWp = sB2 + WFL;
     float* sDWm = sDWp + K * 12;
     float* X = sDWm + K * 12;
-    const int Hin = p.in.H, Win = p.in.W, WS = Win + 2;
+    const int Hin = p.in.H, Win = p.in.W, WS = p.in.Ws;
     const int Hout = p.out.H, Wout = p.out.W;
     const int RS = (2 * p.TR + 1) * WS;
+    const int pin = p.in.pad;                 // frame pad of the input pool (>= 1)
     copy_f4(sBp, p.wp, WFL, G * 128);
     copy_f4(sB1, p.w1, WFL, G * 128);
     copy_f4(sB2, p.w2, WFL, G * 128);
     copy_f4(sDWp, p.wdwp, K * 12, G * 128);
     copy_f4(sDWm, p.wdwm, K * 12, G * 128);
     publish_smem();
+    if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t bp_hi = smem_u32(sBp), bp_lo = smem_u32(sBp + NP * KP);
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
@@ -553,22 +585,27 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
     const int items = p.N * p.bandsPerImg;
     const int grp = threadIdx.x >> 7;
     const unsigned sCo = (unsigned)p.out.sC;
+    uint32_t xparity = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int n = item / p.bandsPerImg;
         const int r0 = (item - n * p.bandsPerImg) * p.TR;
         const int rows = min(p.TR, Hout - r0);
-        const int gr0 = 2 * r0 - 1, nrows = 2 * rows + 1;
-        producers_sync<G>();
-        stage_rows<K, 1, G * 128>(X, RS, WS, p.in, p.tin, n, gr0, nrows);
-        producers_sync<G>();
+        const int gr0 = 2 * r0 - 1, nrows = 2 * rows + 1;       // image rows [gr0, gr0+nrows) <-> staged rows [0, nrows)
+        __syncthreads();
+        publish_smem();
+        if (threadIdx.x == 0) mbar_expect_tx(&xbar, (uint32_t)(K * nrows * WS * sizeof(float)));
+        stage_bulk<K>(X, RS, p.in, p.tin, n, gr0 + pin, nrows, &xbar, 0);
+        mbar_wait(&xbar, xparity);
+        xparity ^= 1u;
         const int npix = rows * Wout;
+        const int coff = pin - 1;
         // ---- proj: dw3x3 s2 + BN -> pw + BN + ReLU on the raw input ---------------------------------------------
         for (int tile = grp; tile * 128 < npix; tile += G) {
             const int q = tile * 128 + g.gtid;
             const bool valid = q < npix;
             const int orow = valid ? q / Wout : 0, ox = valid ? q - orow * Wout : 0;
-            const float* win = X + (2 * orow) * WS + 2 * ox;
-            float* obase = p.out.base + (long long)n * p.out.sN + (long long)(r0 + orow) * Wout + ox;
+            const float* win = X + (2 * orow) * WS + 2 * ox + coff;
+            float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + (r0 + orow) * p.out.Ws + ox;
             pw_tile<KP, NP>(g, bp_hi, bp_lo,
                 [&](int k0, float (&a)[8]) { dw8<3, 2, false>(win, RS, WS, sDWp, k0, valid, a); },
                 [&](int n0, float (&d)[16]) {
@@ -579,15 +616,15 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
                     }
                 });
         }
-        producers_sync<G>();
-        // ---- main pw1 in place on every staged in-image pixel ------------------------------------------------------
+        __syncthreads();
+        // ---- main pw1 in place on every staged in-image pixel (frame / halo positions stay zero) ------------------------
         const int gr_lo = max(gr0, 0), gr_hi = min(gr0 + nrows - 1, Hin - 1);
         const int npos = (gr_hi - gr_lo + 1) * Win;
         for (int tile = grp; tile * 128 < npos; tile += G) {
             const int q = tile * 128 + g.gtid;
             const bool valid = q < npos;
             const int rr = valid ? q / Win : 0, x = valid ? q - rr * Win : 0;
-            float* tpos = X + (gr_lo + rr - gr0) * WS + 1 + x;
+            float* tpos = X + (gr_lo + rr - gr0) * WS + pin + x;
             pw_tile<KP, NP>(g, b1_hi, b1_lo,
                 [&](int k0, float (&a)[8]) {
 #pragma unroll
@@ -601,14 +638,14 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
                     }
                 });
         }
-        producers_sync<G>();
+        __syncthreads();
         // ---- main: dw3x3 s2 + BN -> pw2 + BN + ReLU ---------------------------------------------------------------
         for (int tile = grp; tile * 128 < npix; tile += G) {
             const int q = tile * 128 + g.gtid;
             const bool valid = q < npix;
             const int orow = valid ? q / Wout : 0, ox = valid ? q - orow * Wout : 0;
-            const float* win = X + (2 * orow) * WS + 2 * ox;
-            float* obase = p.out.base + (long long)n * p.out.sN + (long long)(r0 + orow) * Wout + ox;
+            const float* win = X + (2 * orow) * WS + 2 * ox + coff;
+            float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + (r0 + orow) * p.out.Ws + ox;
             pw_tile<KP, NP>(g, b2_hi, b2_lo,
                 [&](int k0, float (&a)[8]) { dw8<3, 2, false>(win, RS, WS, sDWm, k0, valid, a); },
                 [&](int n0, float (&d)[16]) {
@@ -662,10 +699,10 @@ int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout
 int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin, const ChanTab& tout, const float* wdwp, const float* wp,
                  const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s) {
     S2Args a{in, out, tin, tout, wdwp, wp, w1, wdwm, w2, N, 0, 0};
-    const int Hout = out.H, Win = in.W;
+    const int Hout = out.H;
     auto run = [&](auto kern, int KK, int NP, int G) -> int {
         const size_t wfl = (size_t)3 * (2 * NP * KK + 2 * NP) + 2 * KK * 12;
-        auto bytes = [&](int tr) { return (wfl + (size_t)KK * (2 * tr + 1) * (Win + 2) + 4) * sizeof(float); };
+        auto bytes = [&](int tr) { return (wfl + (size_t)KK * (2 * tr + 1) * in.Ws + 4) * sizeof(float); };
         int TR = Hout;
         while (TR > 1 && bytes(TR) > 110 * 1024) --TR;
         a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR;
@@ -723,12 +760,12 @@ int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* t
     DwPwArgs a{};
     for (int b = 0; b < nbranch; ++b) { a.in[b] = in[b]; a.out[b] = out[b]; a.tin[b] = tin[b]; a.tout[b] = tout[b]; a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
     a.N = N; a.nbranch = nbranch; a.nout = 96;
-    const int Hout = out[0].H, Win = in[0].W;
+    const int Hout = out[0].H;
     constexpr int G = 2;
     auto run = [&](auto kern, int S) -> int {
         const size_t wfl = (size_t)(2 * 96 * 96 + 2 * 96) + 96 * 12;
-        dwpw_geometry(a, Hout, wfl + 4, (size_t)96 * (Win + 2), 3, S, out[0].W, G);
-        const size_t bytes = (wfl + (size_t)96 * (S * (a.TR - 1) + 3) * (Win + 2) * a.imgs + 4) * sizeof(float);
+        dwpw_geometry(a, Hout, wfl + 4, (size_t)96 * in[0].Ws, 3, S, out[0].W, G);
+        const size_t bytes = (wfl + (size_t)96 * (S * (a.TR - 1) + 3) * in[0].Ws * a.imgs + 4) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
         const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * nbranch;
         kern<<<min(items, sm_count()), G * 128, bytes, s>>>(a);
@@ -755,13 +792,13 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         a.dstA[0] = obj; a.dstB[0] = cls; a.split[0] = A; a.M[0] = A + C;
         a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
     }
-    const int Hout = sIn.H, Win = sIn.W;
+    const int Hout = sIn.H;
     constexpr int NP = 80, NP2 = 96, G = 2;
     if (A + C > NP2 || 4 * A > NP2) { set_error("tc heads: A+C=%d exceeds the chained tile (%d)", A + C, NP2); return YFV2_EUNSUPPORTED; }
     auto run = [&](auto kern, bool chain) -> int {
         const size_t wfl = (size_t)(2 * NP * 72 + 2 * NP) + (chain ? (size_t)(2 * NP2 * NP + 2 * NP2) : 0) + 72 * 28;
-        dwpw_geometry(a, Hout, wfl + 4, (size_t)72 * (Win + 4), 5, 1, sIn.W, G);
-        const size_t bytes = (wfl + (size_t)72 * (a.TR + 4) * (Win + 4) * a.imgs + 4) * sizeof(float);
+        dwpw_geometry(a, Hout, wfl + 4, (size_t)72 * sIn.Ws, 5, 1, sIn.W, G);
+        const size_t bytes = (wfl + (size_t)72 * (a.TR + 4) * sIn.Ws * a.imgs + 4) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
         const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * 2;
         kern<<<min(items, sm_count()), G * 128, bytes, s>>>(a);

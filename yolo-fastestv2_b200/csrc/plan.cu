@@ -36,6 +36,13 @@ int sm_count() {
     return n;
 }
 
+// pack sizes of the CUDA-core layouts (the depthwise packs inside them feed the tensor-core kernels too)
+size_t shuffle_pack_floats(int K, int stride) {
+    const size_t pwn = pw_pack_floats(K, K), dwn = dw3_pack_floats(K);
+    return stride == 1 ? 2 * pwn + dwn : 3 * pwn + 2 * dwn;
+}
+size_t head_pack_floats() { return 2 * ((size_t)dw5_pack_floats(72) + pw_pack_floats(72, 72)); }
+
 namespace {
 
 constexpr int kStageRepeats[3] = {4, 8, 4};          // shufflenetv2.py:69
@@ -105,7 +112,8 @@ __global__ void gather_kernel(Planes P, ChanTab tab, int Cn, float* __restrict__
     const int p = (int)(i % HW);
     const int c = (int)((i / HW) % Cn);
     const int n = (int)(i / ((long long)HW * Cn));
-    out[i] = plane_ptr(P, n, tab.c[c])[p];
+    const int y = p / P.W, x = p - y * P.W;
+    out[i] = plane_ptr(P, n, tab.c[c])[P.org + y * P.Ws + x];
 }
 
 struct Cursor {           // walks parameters / BN layers in state_dict order
@@ -122,7 +130,10 @@ using namespace yfv2;
 struct yfv2_plan {
     int device, N, H, W, A, C, training;
     int h[4], w[4];                    // strides 4, 8, 16, 32
-    size_t plane[4];                   // plane stride (floats) per resolution
+    size_t plane[4];                   // pool plane stride (floats) per resolution, zero frame of 1 included
+    size_t plane2[4];                  // same with a frame of 2 (inputs of the 5x5 depthwise heads)
+    int ws1[4], ws2[4];                // row strides for the two frame widths
+    const void* ws_zeroed;             // workspace whose frames have been zeroed
     int pool_planes[4];                // 24, 72, 144, 288
     size_t off_pool[4];
     size_t off_s2, off_s3, off_t[4];   // t: cls2, reg2, cls3, reg3 mid-block scratch
@@ -150,14 +161,16 @@ Planes pool_planes(const yfv2_plan* p, float* ws, int r) {
     P.sC = (long long)p->plane[r];
     P.sN = (long long)p->plane[r] * p->pool_planes[r];
     P.H = p->h[r]; P.W = p->w[r];
+    P.Ws = p->ws1[r]; P.pad = 1; P.org = P.Ws + 1;
     return P;
 }
 Planes flat_planes(const yfv2_plan* p, float* ws, size_t off, int r) {
     Planes P;
     P.base = ws + off;
-    P.sC = (long long)p->plane[r];
-    P.sN = (long long)p->plane[r] * kFpnDepth;
+    P.sC = (long long)p->plane2[r];
+    P.sN = (long long)p->plane2[r] * kFpnDepth;
     P.H = p->h[r]; P.W = p->w[r];
+    P.Ws = p->ws2[r]; P.pad = 2; P.org = 2 * P.Ws + 2;
     return P;
 }
 
@@ -225,16 +238,18 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     size_t off = 0;
     for (int r = 0; r < 4; ++r) {
         p->h[r] = H >> (r + 2); p->w[r] = W >> (r + 2);
-        p->plane[r] = align_up((size_t)p->h[r] * p->w[r], 4);
+        p->ws1[r] = (int)align_up(p->w[r] + 2, 4); p->ws2[r] = (int)align_up(p->w[r] + 4, 4);
+        p->plane[r] = (size_t)(p->h[r] + 2) * p->ws1[r];
+        p->plane2[r] = (size_t)(p->h[r] + 4) * p->ws2[r];
         p->pool_planes[r] = pools[r];
         p->off_pool[r] = off;
         off += align_up(p->plane[r] * pools[r] * (size_t)N, 64);
     }
-    p->off_s2 = off; off += align_up(p->plane[2] * kFpnDepth * (size_t)N, 64);
-    p->off_s3 = off; off += align_up(p->plane[3] * kFpnDepth * (size_t)N, 64);
+    p->off_s2 = off; off += align_up(p->plane2[2] * kFpnDepth * (size_t)N, 64);
+    p->off_s3 = off; off += align_up(p->plane2[3] * kFpnDepth * (size_t)N, 64);
     for (int i = 0; i < 4; ++i) {
         p->off_t[i] = off;
-        off += align_up(p->plane[i < 2 ? 2 : 3] * kFpnDepth * (size_t)N, 64);
+        off += align_up(p->plane2[i < 2 ? 2 : 3] * kFpnDepth * (size_t)N, 64);
     }
     p->ws_floats = off;
     build_tables(p);
@@ -260,9 +275,12 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     p->pk_floats = pk;
     for (int i = 0; i < 96; ++i) p->t96.c[i] = 0;   // filled per use (pool-specific offset)
 
-    const char* eng = getenv("YFV2_ENGINE");
-    p->engine = (eng && !strcmp(eng, "ffma")) ? 0 : 1;
-    if (p->engine == 1 && (A + C > 96 || 4 * A > 96)) p->engine = 0;    // chained output-conv tile is 96 wide
+    p->engine = 1;
+    if (A + C > 96 || 4 * A > 96) {
+        set_error("plan_create: anchors+classes = %d exceeds the 96-wide output-conv tile of this build", A + C);
+        delete p;
+        return YFV2_EUNSUPPORTED;
+    }
     auto add = [&](int kind, int a, int b, const char* fmt, int x, int y) {
         yfv2_plan::Stage& st = p->stages[p->n_stages++];
         st.kind = kind; st.a = a; st.b = b;
@@ -270,18 +288,12 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     };
     add(0, 0, 0, "stem", 0, 0);
     for (int b = 0, st = 0, rep = 0; b < kNumBlocks; ++b) {
-        if (p->engine == 0) add(1, b, 0, "stage%d.%d", st + 2, rep);
-        else if (p->blk_K[b] < 96) add(p->blk_stride[b] == 2 ? 11 : 10, b, 0, "stage%d.%d", st + 2, rep);
+        if (p->blk_K[b] < 96) add(p->blk_stride[b] == 2 ? 11 : 10, b, 0, "stage%d.%d", st + 2, rep);
         else { add(12, b, 0, "stage%d.%d/pw1", st + 2, rep); add(13, b, 0, "stage%d.%d/dwpw", st + 2, rep); }
         if (++rep == kStageRepeats[st]) { rep = 0; ++st; }
     }
-    if (p->engine == 0) {
-        add(2, 0, 0, "fpn.S3", 0, 0); add(2, 1, 0, "fpn.S2", 0, 0);
-        for (int lv = 0; lv < 2; ++lv) { add(3, lv, 0, "heads%d.a", lv + 2, 0); add(3, lv, 1, "heads%d.b", lv + 2, 0); }
-    } else {
-        add(14, 1, 0, "fpn.S3", 0, 0); add(14, 2, 0, "fpn.S2", 0, 0);
-        for (int lv = 0; lv < 2; ++lv) { add(15, lv, 0, "heads%d.a", lv + 2, 0); add(15, lv, 1, "heads%d.b", lv + 2, 0); }
-    }
+    add(14, 1, 0, "fpn.S3", 0, 0); add(14, 2, 0, "fpn.S2", 0, 0);
+    for (int lv = 0; lv < 2; ++lv) { add(15, lv, 0, "heads%d.a", lv + 2, 0); add(15, lv, 1, "heads%d.b", lv + 2, 0); }
     p->launches = p->n_stages;
     *out = p;
     return YFV2_OK;
@@ -400,7 +412,7 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
     }
     // output_reg_layers, output_obj_layers, output_cls_layers (detector.py:17-19); obj and cls share one pack
     // the chained output convs contract over the 80-column (72 real) feature tile of the head's second pointwise
-    const bool tc_ok = p->engine == 1;
+    const bool tc_ok = true;
     TRY(pack_pw(cur, false, true, 4 * p->A, kFpnDepth, pk + p->pk_out_reg, round4(4 * p->A), 0, s,
                 tc_ok ? TcDst{pk + p->tk_out_reg, 96, 80} : TcDst{nullptr, 0, 0}));
     const int Moc = round4(p->A + p->C);
@@ -436,15 +448,18 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
     if (first < 0 || last > p->n_stages || first > last) { set_error("forward: bad stage range [%d,%d)", first, last); return YFV2_EINVAL; }
     float* ws = (float*)workspace;
     const float* pk = (const float*)packed;
+    if (p->ws_zeroed != workspace) {
+        // the zero frames around every plane are never written afterwards (kernels store interior pixels only)
+        YFV2_CUDA(cudaMemsetAsync(workspace, 0, p->ws_floats * sizeof(float), s));
+        p->ws_zeroed = workspace;
+    }
     ChanTab ident;
     for (int i = 0; i < kMaxCh; ++i) ident.c[i] = (unsigned short)i;
-    FpnArgs f;
-    f.N = p->N;
+    struct { Planes c3, c2, s3, s2; ChanTab t3, t2; } f;
     f.c3 = pool_planes(p, ws, 3); f.t3 = p->c3;
     f.c2 = pool_planes(p, ws, 2); f.t2 = p->c2;
     f.s3 = flat_planes(p, ws, p->off_s3, 3);
     f.s2 = flat_planes(p, ws, p->off_s2, 2);
-    f.w3 = pk + p->pk_fpn3; f.w2 = pk + p->pk_fpn2;
     for (int si = first; si < last; ++si) {
         const yfv2_plan::Stage& st = p->stages[si];
         const int b = st.a;
@@ -453,35 +468,19 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
             TRY(launch_stem(a, s));
         } break;
-        case 1: {
-            ShuffleArgs a;
-            a.K = p->blk_K[b]; a.stride = p->blk_stride[b]; a.N = p->N;
-            a.out = pool_planes(p, ws, p->blk_res[b]);
-            a.in = a.stride == 2 ? pool_planes(p, ws, p->blk_res[b] - 1) : a.out;
-            a.tin = p->tin[b]; a.tout = p->tout[b];
-            a.wpack = pk + p->pk_block[b];
-            TRY(launch_shuffle(a, s));
-        } break;
-        case 2: TRY(launch_fpn(f, st.a, s)); break;
-        case 3: case 15: {
+        case 15: {
             const int lv = st.a, half = st.b;
-            HeadArgs h;
-            h.N = p->N; h.A = p->A; h.C = p->C;
-            h.s = lv ? f.s3 : f.s2;
-            h.t_cls = flat_planes(p, ws, p->off_t[2 * lv], 2 + lv);
-            h.t_reg = flat_planes(p, ws, p->off_t[2 * lv + 1], 2 + lv);
-            h.w_cls = pk + p->pk_head[2 * lv];
-            h.w_reg = pk + p->pk_head[2 * lv + 1];
-            h.w_out_reg = pk + p->pk_out_reg;
-            h.w_out_oc = pk + p->pk_out_oc;
-            h.reg = preds[3 * lv]; h.obj = preds[3 * lv + 1]; h.cls = preds[3 * lv + 2];
-            if (st.kind == 3) { TRY(launch_heads(h, half, s)); break; }
-            // tensor-core heads: DW pack = first 72*28 floats of each half of the FFMA head pack
+            const Planes sIn = lv ? f.s3 : f.s2;
+            const Planes t_cls = flat_planes(p, ws, p->off_t[2 * lv], 2 + lv);
+            const Planes t_reg = flat_planes(p, ws, p->off_t[2 * lv + 1], 2 + lv);
+            const float* w_cls = pk + p->pk_head[2 * lv];
+            const float* w_reg = pk + p->pk_head[2 * lv + 1];
+            // DW pack = first 72*28 floats of each half of the head pack
             const size_t half_off = (size_t)half * (dw5_pack_floats(kFpnDepth) + pw_pack_floats(kFpnDepth, kFpnDepth));
-            const float* wdw[2] = {h.w_cls + half_off, h.w_reg + half_off};
+            const float* wdw[2] = {w_cls + half_off, w_reg + half_off};
             const float* wpw[2] = {pk + p->tk_head[2 * lv][half], pk + p->tk_head[2 * lv + 1][half]};
-            TRY(tc_launch_heads(half, h.s, h.t_cls, h.t_reg, wdw, wpw, pk + p->tk_out_oc, pk + p->tk_out_reg, h.reg, h.obj, h.cls,
-                                p->A, p->C, p->N, s));
+            TRY(tc_launch_heads(half, sIn, t_cls, t_reg, wdw, wpw, pk + p->tk_out_oc, pk + p->tk_out_reg, preds[3 * lv], preds[3 * lv + 1],
+                                preds[3 * lv + 2], p->A, p->C, p->N, s));
         } break;
         case 10: {   // tc fused stride-1 block
             const int K = p->blk_K[b];
