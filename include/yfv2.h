@@ -116,6 +116,22 @@ YFV2_API int yfv2_detect_u8_host(yfv2_plan* plan, const uint8_t* x_host, const v
                         float* out_host, int* counts_host, void* workspace, void* stream);
 YFV2_API size_t yfv2_detect_workspace_bytes(const yfv2_plan* plan, int max_det);
 
+/* ---- compute_loss (utils/loss.py:130-208) with build_target (:53-124) and CIoU (:8-51) ---------------------------
+ * preds: the six head tensors (as returned by yfv2_forward or by any other model), targets: device [nt,6] fp32 rows
+ * (img_idx, cls, cx, cy, w, h) normalised; anchors_host as for yfv2_decode.  losses: device float[4] =
+ * (lbox*3.2, lobj*64, lcls*32, sum) — the four values the reference returns.  dpreds (optional, may be NULL): six
+ * tensors shaped like preds receiving d(loss)/d(preds) (what loss.backward() would put into the head tensors).
+ * Asynchronous on `stream`; workspace from yfv2_loss_workspace_bytes. */
+YFV2_API int yfv2_loss_workspace_bytes(int N, int H, int W, int A, int C, int nt, size_t* bytes);
+YFV2_API int yfv2_compute_loss(const float* const preds[6], const float* targets, int nt, int N, int H, int W, int A, int C,
+                               const double* anchors_host, float* losses, float* const dpreds[6], void* workspace,
+                               void* stream);
+/* test hook: copy out the matched rows of one pyramid level in the reference's order (offset type, anchor, target):
+ * idx = device int32 [4][5*A*nt] rows (b, a, gj, gi), tbox device [.,4] fp32, anch device [.,2] fp64, tcls device int32.
+ * Synchronises `stream` to return the row count. */
+YFV2_API int yfv2_loss_read_targets(const void* workspace, int level, int N, int H, int W, int A, int nt, int* count_host,
+                                    int* idx, float* tbox, double* anch, int* tcls, void* stream);
+
 /* ---- stage-granular forward (profiling / tests) ---------------------------------------------------------
  * A forward is yfv2_plan_forward_launches() fused stages, one kernel launch each; yfv2_plan_stage_name(i) names
  * them ("stem", "stage2.0", ..., "stage4.1/pw1", "stage4.1/dwpw", "fpn.S3", "fpn.S2", "heads2.a", ...).

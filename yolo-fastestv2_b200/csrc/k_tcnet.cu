@@ -185,26 +185,34 @@ template <int KS, int S, bool RELU>
 __device__ __forceinline__ void dw8(const float* __restrict__ win, int RS, int WS, const float* __restrict__ wdw, int k0, bool valid,
                                     float (&a)[8]) {
     constexpr int R = KS == 3 ? 12 : 28;
+    if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+        return;
+    }
+    const float* xk = win + k0 * RS;
+    const float* wk = wdw + k0 * R;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float* wk = wdw + (k0 + j) * R;
         float w[R];
 #pragma unroll
         for (int t = 0; t < R / 4; ++t) {
             const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * t);
             w[4 * t] = w4.x; w[4 * t + 1] = w4.y; w[4 * t + 2] = w4.z; w[4 * t + 3] = w4.w;
         }
-        const float* xk = win + (k0 + j) * RS;
         float d = 0.f;
-        if (valid) {
+        const float* row = xk;
 #pragma unroll
-            for (int dy = 0; dy < KS; ++dy)
+        for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
-                for (int dx = 0; dx < KS; ++dx) d = fmaf(w[dy * KS + dx], xk[dy * WS + dx], d);
-            d = fmaf(d, w[KS * KS], w[KS * KS + 1]);
-            if (RELU) d = fmaxf(d, 0.f);
+            for (int dx = 0; dx < KS; ++dx) d = fmaf(w[dy * KS + dx], row[dx], d);
+            row += WS;
         }
+        d = fmaf(d, w[KS * KS], w[KS * KS + 1]);
+        if (RELU) d = fmaxf(d, 0.f);
         a[j] = d;
+        xk += RS;
+        wk += R;
     }
 }
 

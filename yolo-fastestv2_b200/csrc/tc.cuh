@@ -111,12 +111,15 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
 }
 
 // Split 8 fp32 values and store them as 8 columns of A_hi (at col) and A_lo (at col + lo_off) for this thread's lane.
+// hi keeps the top 19 bits (sign, exponent, 10 mantissa bits) so it is exactly a tf32 value; lo = a - hi is exact in fp32
+// (|lo| < 2^-10 |a|) and is handed over as is — the tensor core reads its top 19 bits, leaving a residual below
+// 2^-20 |a| per operand.  Two instructions per element instead of two emulated cvt.rna.tf32.
 __device__ __forceinline__ void store_a8(uint32_t taddr_hi, uint32_t lo_off, const float (&a)[8]) {
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        hi[i] = tf32_rna(a[i]);
-        lo[i] = tf32_rna(a[i] - __uint_as_float(hi[i]));
+        hi[i] = __float_as_uint(a[i]) & 0xFFFFE000u;
+        lo[i] = __float_as_uint(a[i] - __uint_as_float(hi[i]));
     }
     tmem_st8(taddr_hi, hi);
     tmem_st8(taddr_hi + lo_off, lo);

@@ -51,6 +51,13 @@ PROTOTYPES = {
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_detect_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_int]),
+    "yfv2_loss_workspace_bytes": (ctypes.c_int, [ctypes.c_int] * 6 + [ctypes.POINTER(ctypes.c_size_t)]),
+    "yfv2_compute_loss": (ctypes.c_int, [_c_void_pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, _c_void_pp,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_loss_read_targets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_plan_stage_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
     "yfv2_forward_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _c_void_pp,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
@@ -285,3 +292,47 @@ def debug_pw_tc(x, w):
                                       ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), K, N, P, _stream(x.device)),
                "debug_pw_tc")
     return out
+
+
+def compute_loss(preds, targets, cfg, want_grads=True, return_workspace=False):
+    """utils.loss.compute_loss on the device.  Returns (losses[4] CUDA tensor, dpreds 6-tuple or None[, workspace])."""
+    for p in preds:
+        _require_cuda(p, "preds")
+    preds = [p.detach().contiguous().float() for p in preds]
+    N, A4, h, w = preds[0].shape
+    A, C = preds[1].shape[1], preds[2].shape[1]
+    H, W = h * 16, w * 16
+    dev = preds[0].device
+    targets = targets.detach().to(dev).float().contiguous().reshape(-1, 6)
+    nt = targets.shape[0]
+    nb = ctypes.c_size_t()
+    _check(lib().yfv2_loss_workspace_bytes(N, H, W, A, C, nt, ctypes.byref(nb)), "loss_workspace_bytes")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    dpreds = [torch.empty_like(p) for p in preds] if want_grads else None
+    with torch.cuda.device(dev):
+        _check(lib().yfv2_compute_loss(_ptr_array(preds), ctypes.c_void_p(targets.data_ptr()) if nt else None, nt, N, H, W, A, C,
+                                       anchors_array(cfg), ctypes.c_void_p(losses.data_ptr()),
+                                       _ptr_array(dpreds) if want_grads else None, ctypes.c_void_p(ws.data_ptr()), _stream(dev)),
+               "compute_loss")
+    out = (losses, tuple(dpreds) if want_grads else None)
+    return out + ((ws, (N, H, W, A, nt)),) if return_workspace else out
+
+
+def read_targets(ws_info, level):
+    """Matched rows of one level after compute_loss(..., return_workspace=True): (idx[4,m], tbox[m,4], anch[m,2], tcls[m])."""
+    ws, (N, H, W, A, nt) = ws_info
+    cap = 5 * A * max(nt, 1)
+    dev = ws.device
+    idx = torch.zeros((4, cap), dtype=torch.int32, device=dev)
+    tbox = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
+    anch = torch.zeros((cap, 2), dtype=torch.float64, device=dev)
+    tcls = torch.zeros((cap,), dtype=torch.int32, device=dev)
+    cnt = ctypes.c_int()
+    with torch.cuda.device(dev):
+        _check(lib().yfv2_loss_read_targets(ctypes.c_void_p(ws.data_ptr()), level, N, H, W, A, nt, ctypes.byref(cnt),
+                                            ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(tbox.data_ptr()),
+                                            ctypes.c_void_p(anch.data_ptr()), ctypes.c_void_p(tcls.data_ptr()), _stream(dev)),
+               "loss_read_targets")
+    m = cnt.value
+    return idx[:, :m], tbox[:m], anch[:m], tcls[:m]
