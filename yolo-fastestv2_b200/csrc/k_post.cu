@@ -10,6 +10,9 @@
 // strict '>' filters, box = xy -/+ wh/2, class offset cls*4096 added in fp32, IoU = inter/(a+b-inter)
 // in fp32 compared as double against the threshold, stable descending order (ties by original row),
 // and no FMA contraction anywhere in that arithmetic — every step uses the __f*_rn intrinsics.
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace yfv2 {
@@ -151,6 +154,8 @@ decode_kernel(PostGeom g, float* __restrict__ out, int chunks0) {
 struct NmsParams {
     float conf_thres;
     double iou_thres;
+    double iou_mid;    // fl32(q) > iou_thres  <=>  q > iou_mid (or >= when iou_tie_up), see iou_gt()
+    int iou_tie_up;
     const int* class_filter;
     int n_filter;
     int max_det;
@@ -210,23 +215,38 @@ __device__ __forceinline__ bool class_ok(const NmsParams& p, int cls) {
     return ok;
 }
 
-// xywh -> xyxy (utils/utils.py:67-74) and push; called by one lane.
-__device__ __forceinline__ void push_candidate(const NmsSmem& s, float cx, float cy, float w, float h, float conf, int cls,
-                                               int row) {
-    const unsigned int slot = atomicAdd(&s.misc[0], 1u);
+// xywh -> xyxy (utils/utils.py:67-74) and store candidate `slot`; called by the lane that owns the candidate.
+__device__ __forceinline__ void write_candidate(const NmsSmem& s, unsigned int slot, float cx, float cy, float w, float h, float conf,
+                                                int cls, int row) {
     const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
     s.cbox[slot] = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
     s.ccls[slot] = (unsigned short)cls;
     s.keys[slot] = ((unsigned long long)f2sortable(conf) << 32) |
                    ((unsigned long long)(0xFFFFu - (unsigned)row) << 16) | (unsigned long long)slot;
 }
+// Warp-aggregated slot allocation: one shared-memory atomic per warp call instead of one per candidate.  All 32 lanes call.
+__device__ __forceinline__ unsigned int alloc_slots(const NmsSmem& s, bool want) {
+    const unsigned int bal = __ballot_sync(0xffffffffu, want);
+    unsigned int base = 0;
+    if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&s.misc[0], (unsigned int)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+}
 
-__device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& b, float ab, double thr) {
+// torchvision: ovr = inter / (a_i + a_j - inter) in fp32, suppressed iff (double)ovr > thr.  The fp32 quotient exceeds thr
+// iff the real quotient lies beyond the rounding boundary `mid` between the two floats that bracket thr, so for a positive
+// finite denominator the test is inter > mid*u (>= when the tie rounds up) — both sides exact in fp64 (24-bit x 25-bit
+// product) — and the IEEE division subroutine is only needed for degenerate denominators.  Bit-exact by construction.
+__device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& b, float ab, const NmsParams& p) {
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
-    return (double)ovr > thr;
+    const float u = __fsub_rn(__fadd_rn(aa, ab), inter);
+    if (u > 0.f && u < 3.0e38f && inter < 3.0e38f) {
+        const double lhs = (double)inter, rhs = __dmul_rn(p.iou_mid, (double)u);
+        return p.iou_tie_up ? lhs >= rhs : lhs > rhs;
+    }
+    return (double)__fdiv_rn(inter, u) > p.iou_thres;
 }
 
 __device__ void bitonic_sort_desc(unsigned long long* keys, int n2) {
@@ -280,7 +300,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
                 const float4 bj = s.chbox[j];
                 const float aj = s.charea[j];
                 bool dead = false;
-                for (int i = q; i < nk && !dead; i += NT / kNmsChunk) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p.iou_thres);
+                for (int i = q; i < nk && !dead; i += NT / kNmsChunk) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
                 if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
             }
         }
@@ -293,7 +313,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
 #pragma unroll 4
                 for (int e = 0; e < 16; ++e) {
                     const int j = jq * 16 + e;
-                    if (j > i && j < cn && iou_gt(bi, ai, s.chbox[j], s.charea[j], p.iou_thres)) bits |= 1u << e;
+                    if (j > i && j < cn && iou_gt(bi, ai, s.chbox[j], s.charea[j], p)) bits |= 1u << e;
                 }
                 if (bits) atomicOr(&s.cmask[2 * i + (jq >> 1)], bits << ((jq & 1) * 16));
             }
@@ -359,8 +379,10 @@ nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
             if (v > best) { best = v; bi = c; }
         }
         warp_argmax(best, bi);                                        // :267 first max
-        if (lane == 0 && best > p.conf_thres && class_ok(p, bi))      // :268, :271-272
-            push_candidate(s, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r);
+        if (lane == 0 && best > p.conf_thres && class_ok(p, bi)) {    // :268, :271-272
+            const unsigned int slot = atomicAdd(&s.misc[0], 1u);
+            write_candidate(s, slot, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r);
+        }
     }
     sort_and_suppress(s, p, n);
 }
@@ -385,6 +407,9 @@ decode_nms_kernel(PostGeom g, NmsParams p) {
             for (int cl = warp; cl < ncell; cl += NT / 32) {
                 CellRegs r;
                 decode_cell(S, g, lv, cell0 + cl, cl, lane, r);
+                float my_conf = 0.f;
+                int my_cls = 0;
+                bool my_want = false;
                 for (int a = 0; a < A; ++a) {
                     const float obj = __shfl_sync(0xffffffffu, r.ob, a);
                     if (!(obj > p.conf_thres)) continue;
@@ -399,9 +424,10 @@ decode_nms_kernel(PostGeom g, NmsParams p) {
                         }
                     }
                     warp_argmax(best, bi);
-                    if (lane == a && best > p.conf_thres && class_ok(p, bi))
-                        push_candidate(s, r.bx, r.by, r.bw, r.bh, best, bi, row0 + (cell0 + cl) * A + a);
+                    if (lane == a && best > p.conf_thres && class_ok(p, bi)) { my_want = true; my_conf = best; my_cls = bi; }
                 }
+                const unsigned int slot = alloc_slots(s, my_want);
+                if (my_want) write_candidate(s, slot, r.bx, r.by, r.bw, r.bh, my_conf, my_cls, row0 + (cell0 + cl) * A + lane);
             }
         }
     }
@@ -435,6 +461,14 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
     if (!out || !counts || max_det <= 0 || max_det > 4096 || M <= 0) { set_error("nms: bad arguments"); return YFV2_EINVAL; }
     if (M > YFV2_NMS_MAX_CAND) { set_error("nms: M=%d candidates per image exceeds %d", M, YFV2_NMS_MAX_CAND); return YFV2_EUNSUPPORTED; }
     p.conf_thres = conf_thres; p.iou_thres = iou_thres;
+    {   // rounding boundary of the fp32 quotient around the (double) threshold
+        float f0 = (float)iou_thres;                       // nearest float
+        if ((double)f0 > iou_thres) f0 = nextafterf(f0, -INFINITY);
+        const float f1 = nextafterf(f0, INFINITY);          // smallest float > thr
+        p.iou_mid = ((double)f0 + (double)f1) * 0.5;
+        unsigned int bits; memcpy(&bits, &f1, 4);
+        p.iou_tie_up = (bits & 1u) == 0u;                   // ties-to-even: the midpoint rounds to f1 iff f1 is even
+    }
     p.class_filter = n_filter > 0 ? class_filter : nullptr; p.n_filter = n_filter;
     p.max_det = max_det; p.max_wh = max_wh; p.out = out; p.counts = counts; p.kept_idx = kept_idx; p.M = M;
     p.MCp = 64;
