@@ -80,3 +80,22 @@ def test_load_datafile(tmp_path):
     assert (cfg["width"], cfg["height"], cfg["anchor_num"], cfg["batch_size"]) == (352, 352, 3, 128)
     assert set(cfg) == {"model_name", "epochs", "steps", "batch_size", "subdivisions", "learning_rate", "pre_weights",
                         "classes", "width", "height", "anchor_num", "anchors", "val", "train", "names"}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/utils"), reason="reference checkout not present (build container only)")
+def test_overlay_resolves_out_of_scope_names_from_the_reference():
+    """With the reference checkout behind the mirror on sys.path, utils.datasets / utils.utils.evaluation come from the
+    reference while the hot-path functions stay ours (what train.py / evaluation.py need to run unchanged)."""
+    import subprocess, sys as _sys, textwrap
+    code = textwrap.dedent("""
+        import sys, types
+        ts = types.ModuleType("torchsummary"); ts.summary = lambda *a, **k: None; sys.modules["torchsummary"] = ts
+        sys.path.insert(0, "/root/reference"); sys.path.insert(0, "%s")
+        import utils.utils as uu, utils.datasets as ud, utils.loss as ul, model.detector as md
+        assert "yolo-fastestv2_b200" in uu.__file__ and "yolo-fastestv2_b200" in ul.__file__ and "yolo-fastestv2_b200" in md.__file__
+        assert ud.__file__.startswith("/root/reference") and hasattr(ud, "TensorDataset") and hasattr(ud, "collate_fn")
+        assert callable(uu.evaluation) and uu.evaluation.__globals__["non_max_suppression"] is uu.non_max_suppression
+        print("ok")
+    """ % os.path.join(ROOT, "yolo-fastestv2_b200"))
+    r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -147,7 +147,7 @@ struct yfv2_plan {
     // tensor-core engine
     int engine;                        // 0 = FFMA kernels (k_shuffle/k_fpn/k_head), 1 = tcgen05 kernels (k_tcnet)
     size_t tk_blk[kNumBlocks][3];      // tc packs per block: [0]=pw1 [1]=pw2 [2]=proj pw (stride-2 only)
-    size_t tk_fpn3, tk_fpn2, tk_head[4][2], tk_out_oc, tk_out_reg;
+    size_t tk_stem, tk_fpn3, tk_fpn2, tk_head[4][2], tk_out_oc, tk_out_reg;
     ChanTab t96;                       // scratch plane ids for the K=96 blocks' pw1 output
     int n_stages;
     struct Stage { int kind, a, b; char name[24]; } stages[64];
@@ -267,6 +267,7 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
         const int n = p->blk_stride[b] == 2 ? 3 : 2;
         for (int i = 0; i < n; ++i) { p->tk_blk[b][i] = pk; pk += align_up(2 * (size_t)NP * K + 2 * NP, 4); }
     }
+    p->tk_stem = pk; pk += align_up(2 * 32 * 32 + 64, 4);
     p->tk_fpn3 = pk; pk += align_up(2 * 80 * 192 + 160, 4);
     p->tk_fpn2 = pk; pk += align_up(2 * 80 * 288 + 160, 4);
     for (int i = 0; i < 4; ++i) for (int h = 0; h < 2; ++h) { p->tk_head[i][h] = pk; pk += align_up(2 * 80 * 72 + 160, 4); }
@@ -377,7 +378,7 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
     YFV2_CUDA(cudaMemsetAsync(pk, 0, p->pk_floats * sizeof(float), s));
     Cursor cur{params, bn_running};
     // backbone.first_conv (shufflenetv2.py:74-78)
-    TRY(pack_pw(cur, true, false, 24, 27, pk + p->pk_stem, 24, 0, s));
+    TRY(pack_pw(cur, true, false, 24, 27, pk + p->pk_stem, 24, 0, s, TcDst{pk + p->tk_stem, 32, 32}));
     for (int b = 0; b < kNumBlocks; ++b) {
         const int K = p->blk_K[b];
         float* d = pk + p->pk_block[b];
@@ -426,6 +427,7 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
 }
 
 namespace yfv2 {
+int tc_launch_stem(const void* x, int is_u8, const Planes& out, const float* wpack, int N, int H, int W, cudaStream_t s);
 int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout, const float* w1, const float* wdw, const float* w2,
                  int N, cudaStream_t s);
 int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin, const ChanTab& tout, const float* wdwp, const float* wp,
@@ -465,8 +467,12 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
         const int b = st.a;
         switch (st.kind) {
         case 0: {
-            StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
-            TRY(launch_stem(a, s));
+            if (getenv("YFV2_STEM_FFMA")) {
+                StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
+                TRY(launch_stem(a, s));
+            } else {
+                TRY(tc_launch_stem(x, is_u8, pool_planes(p, ws, 0), pk + p->tk_stem, p->N, p->H, p->W, s));
+            }
         } break;
         case 15: {
             const int lv = st.a, half = st.b;

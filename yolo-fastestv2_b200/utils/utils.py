@@ -70,3 +70,30 @@ def detect(preds, cfg, conf_thres=0.3, iou_thres=0.45, classes=None):
     """Fused handel_preds + non_max_suppression: same list-of-[n_i,6] result without the candidate tensor."""
     out, counts, _ = yfv2_engine.decode_nms(preds, cfg, conf_thres, iou_thres, classes)
     return _to_list(out, counts)
+
+
+# ---- everything else of the reference's utils/utils.py (mAP bookkeeping: evaluation, get_batch_statistics, ap_per_class,
+# compute_ap, bbox_iou, xywh2xyxy — CPU code outside the hot path, SURVEY 2.1 #10) is taken from the reference checkout
+# when it is on sys.path, re-pointed at the CUDA hot-path functions above so `utils.utils.evaluation(...)` runs them.
+def _overlay_reference():
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in list(sys.path):
+        cand = os.path.join(os.path.abspath(p or "."), "utils", "utils.py")
+        if os.path.isfile(cand) and os.path.dirname(cand) != here:
+            try:
+                spec = importlib.util.spec_from_file_location("_yfv2_reference_utils", cand)
+                ref = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(ref)
+            except Exception:          # a reference that cannot be imported here (missing cv2/tqdm) is simply not overlaid
+                return None
+            for name in ("handel_preds", "non_max_suppression", "load_datafile"):
+                setattr(ref, name, globals()[name])
+            for name in dir(ref):
+                if not name.startswith("_") and name not in globals():
+                    globals()[name] = getattr(ref, name)
+            return ref
+    return None
+
+
+_reference_utils = _overlay_reference()
