@@ -130,6 +130,19 @@ __device__ __forceinline__ void pw_tile(Grp& g, uint32_t b_hi, uint32_t b_lo, Lo
     get_tile<NP>(g, static_cast<Epi&&>(epi));
 }
 
+// Same with the chunk loop NOT unrolled: for loaders that accept a runtime k0 (the depthwise stencils).  The fully
+// unrolled 72-channel 5x5 stencil is ~100 KB of SASS and starves the instruction cache with 8 warps per SM.
+template <int KP, int NP, class Loader, class Epi>
+__device__ __forceinline__ void pw_tile_rolled(Grp& g, uint32_t b_hi, uint32_t b_lo, Loader&& load, Epi&& epi) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < KP; k0 += 8) {
+        float a[8];
+        load(k0, a);
+        put_chunk<KP, NP>(g, a, k0 >> 3, b_hi, b_lo);
+    }
+    get_tile<NP>(g, static_cast<Epi&&>(epi));
+}
+
 // CTA prologue: TMEM allocation, barrier init.
 template <int G, int COLS>
 __device__ __forceinline__ Grp cta_setup(Pipe* pipes, uint32_t* tmem_slot) {
@@ -204,14 +217,17 @@ __device__ __forceinline__ void dw8(const float* __restrict__ win, int RS, int W
             const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * t);
             w[4 * t] = w4.x; w[4 * t + 1] = w4.y; w[4 * t + 2] = w4.z; w[4 * t + 3] = w4.w;
         }
-        float d = 0.f;
+        // one independent partial sum per kernel row (breaks the 9- / 25-long dependent FMA chain), then a short add tree
+        float pr[KS];
         const float* row = xk;
 #pragma unroll
         for (int dy = 0; dy < KS; ++dy) {
+            pr[dy] = w[dy * KS] * row[0];
 #pragma unroll
-            for (int dx = 0; dx < KS; ++dx) d = fmaf(w[dy * KS + dx], row[dx], d);
+            for (int dx = 1; dx < KS; ++dx) pr[dy] = fmaf(w[dy * KS + dx], row[dx], pr[dy]);
             row += WS;
         }
+        float d = KS == 3 ? (pr[0] + pr[1]) + pr[2] : ((pr[0] + pr[1]) + (pr[2] + pr[3])) + pr[KS - 1];
         d = fmaf(d, w[KS * KS], w[KS * KS + 1]);
         if (RELU) d = fmaxf(d, 0.f);
         a[j] = d;
@@ -387,7 +403,7 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
             const float* win = X + im * RS1 + (S * orow) * WS + S * ox + coff;
             if (!CHAIN) {
                 float* obase = p.out[br].base + (long long)n * p.out[br].sN + p.out[br].org + (r0 + orow) * p.out[br].Ws + ox;
-                pw_tile<KP, NP>(g, b_hi, b_lo,
+                pw_tile_rolled<KP, NP>(g, b_hi, b_lo,
                     [&](int k0, float (&a)[8]) { dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a); },
                     [&](int n0, float (&d)[16]) {
                         if (valid) {
@@ -404,11 +420,11 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
                     });
             } else {
                 // features (NP columns, p.nout real) -> BN -> second contraction against the output conv -> dense NCHW.
-#pragma unroll
+#pragma unroll 1
                 for (int k0 = 0; k0 < KP; k0 += 8) {
                     float a[8];
                     dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a);
-                    put_chunk<KP, NP>(g, a, k0 / 8, b_hi, b_lo);
+                    put_chunk<KP, NP>(g, a, k0 >> 3, b_hi, b_lo);
                 }
                 float f[NP];
                 get_tile<NP>(g, [&](int n0, float (&d)[16]) {
@@ -541,7 +557,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
             const int orow = valid ? q / W : 0, ox = valid ? q - orow * W : 0;
             const float* win = T + orow * WS + ox;
             float* obase = p.P.base + (long long)n * p.P.sN + p.P.org + (r0 + orow) * p.P.Ws + ox;
-            pw_tile<KP, NP>(g, b2_hi, b2_lo,
+            pw_tile_rolled<KP, NP>(g, b2_hi, b2_lo,
                 [&](int k0, float (&a)[8]) { dw8<3, 1, false>(win, RS, WS, sDW, k0, valid, a); },
                 [&](int n0, float (&d)[16]) {
                     if (valid) {
@@ -628,7 +644,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
             const int orow = valid ? q / Wout : 0, ox = valid ? q - orow * Wout : 0;
             const float* win = X + (2 * orow) * WS + 2 * ox + coff;
             float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + (r0 + orow) * p.out.Ws + ox;
-            pw_tile<KP, NP>(g, bp_hi, bp_lo,
+            pw_tile_rolled<KP, NP>(g, bp_hi, bp_lo,
                 [&](int k0, float (&a)[8]) { dw8<3, 2, false>(win, RS, WS, sDWp, k0, valid, a); },
                 [&](int n0, float (&d)[16]) {
                     if (valid) {
@@ -668,7 +684,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
             const int orow = valid ? q / Wout : 0, ox = valid ? q - orow * Wout : 0;
             const float* win = X + (2 * orow) * WS + 2 * ox + coff;
             float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + (r0 + orow) * p.out.Ws + ox;
-            pw_tile<KP, NP>(g, b2_hi, b2_lo,
+            pw_tile_rolled<KP, NP>(g, b2_hi, b2_lo,
                 [&](int k0, float (&a)[8]) { dw8<3, 2, false>(win, RS, WS, sDWm, k0, valid, a); },
                 [&](int n0, float (&d)[16]) {
                     if (valid) {
