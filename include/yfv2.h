@@ -132,6 +132,32 @@ YFV2_API int yfv2_compute_loss(const float* const preds[6], const float* targets
 YFV2_API int yfv2_loss_read_targets(const void* workspace, int level, int N, int H, int W, int A, int nt, int* count_host,
                                     int* idx, float* tbox, double* anch, int* tcls, void* stream);
 
+/* ---- training operators (train-mode forward with batch-statistics BatchNorm, and the backward of every op) --------
+ * Dense NCHW fp32 device tensors; composed into the network by the Python mirror's autograd Functions
+ * (yolo-fastestv2_b200/model/train_ops.py).  Reference: what autograd does for train.py:105-110.
+ *   conv1x1:  y[n][m][p] = sum_k w[m][k] x[n][k][p] (+bias);  bwd outputs are optional (NULL to skip).
+ *   dwconv:   depthwise ks x ks (3|5), stride 1|2, pad ks/2.   stem: dense 3x3 s2 p1 with 3 input channels.
+ *   bn_train: batch statistics over (N, HW), running-stat update (momentum 0.1, unbiased var), optional fused ReLU;
+ *             scratch = 2*C doubles; save_mean / save_invstd feed the backward.
+ *   maxpool:  3x3 s2 p1 with argmax indices;  upsample2: nearest x2. */
+YFV2_API int yfv2_op_conv1x1_fwd(const float* x, const float* w, const float* bias, float* y, int N, int K, int M, int HW, void* stream);
+YFV2_API int yfv2_op_conv1x1_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, int N, int K, int M,
+                                 int HW, void* stream);
+YFV2_API int yfv2_op_dwconv_fwd(const float* x, const float* w, float* y, int N, int C, int H, int W, int ks, int stride, void* stream);
+YFV2_API int yfv2_op_dwconv_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int N, int C, int H, int W, int ks,
+                                int stride, void* stream);
+YFV2_API int yfv2_op_stem_fwd(const float* x, const float* w, float* y, int N, int M, int H, int W, void* stream);
+YFV2_API int yfv2_op_stem_wgrad(const float* x, const float* dy, float* dw, int N, int M, int H, int W, void* stream);
+YFV2_API int yfv2_op_bn_train_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float* y,
+                                  float* save_mean, float* save_invstd, double* scratch, int N, int C, int HW, int relu, void* stream);
+YFV2_API int yfv2_op_bn_train_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                                  const float* save_invstd, float* dx, float* dgamma, float* dbeta, double* scratch, int N, int C, int HW,
+                                  int relu, void* stream);
+YFV2_API int yfv2_op_maxpool_fwd(const float* x, float* y, int* idx, int planes, int H, int W, void* stream);
+YFV2_API int yfv2_op_maxpool_bwd(const float* dy, const int* idx, float* dx, int planes, int H, int W, void* stream);
+YFV2_API int yfv2_op_upsample2_fwd(const float* x, float* y, int planes, int H, int W, void* stream);
+YFV2_API int yfv2_op_upsample2_bwd(const float* dy, float* dx, int planes, int H, int W, void* stream);
+
 /* ---- stage-granular forward (profiling / tests) ---------------------------------------------------------
  * A forward is yfv2_plan_forward_launches() fused stages, one kernel launch each; yfv2_plan_stage_name(i) names
  * them ("stem", "stage2.0", ..., "stage4.1/pw1", "stage4.1/dwpw", "fpn.S3", "fpn.S2", "heads2.a", ...).

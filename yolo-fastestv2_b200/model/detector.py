@@ -63,7 +63,10 @@ class Detector(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("yfv2 Detector runs on CUDA only (no CPU fallback); move the model and input to a GPU")
         if self.training:
-            raise NotImplementedError("train-mode forward/backward kernels are not part of this build yet; call .eval()")
+            if self.export_onnx:
+                raise NotImplementedError("export_onnx=True is an inference-only head")
+            from model import train_ops
+            return train_ops.forward_train(self, x.float() if x.dtype != torch.float32 else x)
         if self.export_onnx:
             raise NotImplementedError("export_onnx=True head (sigmoid/softmax + NHWC concat) is not part of this build yet")
         if x.dim() != 4 or x.shape[1] != 3:
