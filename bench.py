@@ -298,8 +298,15 @@ def run_ours(args, rank, world, local_rank):
         bb = [s for s in stages if s["stage"].startswith(("stem", "stage"))]
         bb_bytes = sum(s["alg_MB"] for s in bb) * 1e6
         bb_us = sum(s["us"] for s in bb)
+        traffic = None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f)["per_launch_bytes"].get(top["stage"])
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": top["stage"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": top["frac"], "traffic": None, "peak_source": peak_src, "timing": "CUDA events, L2 flushed before each launch",
+                "frac": top["frac"], "traffic": traffic, "algorithmic_bytes": int(top["alg_MB"] * 1e6),
+                "peak_source": peak_src + " (of measured)", "timing": "CUDA events, L2 flushed before each launch",
                 "backbone": {"achieved": round(bb_bytes / (bb_us * 1e-6) / 1e9, 1), "frac": round(bb_bytes / (bb_us * 1e-6) / 1e9 / peak, 4),
                              "us": round(bb_us, 1)}}
         del flush

@@ -21,7 +21,6 @@
 #include "tc.cuh"
 
 namespace yfv2 {
-__device__ long long g_dbg_ts[64];     // phase timestamps of CTA 0 / thread 0 (profiling aid)
 namespace {
 
 using namespace tc;
@@ -104,11 +103,9 @@ __device__ __forceinline__ void put_chunk(Grp& g, const float (&a)[8], int c, ui
 // Collect the NP output columns of this thread's pixel.
 template <int NP, class Epi>
 __device__ __forceinline__ void get_tile(Grp& g, Epi&& epi) {
-    if (blockIdx.x == 0 && threadIdx.x == 0 && g_dbg_ts[62] < 8) g_dbg_ts[16 + 3 * g_dbg_ts[62]] = clock64();
     mbar_wait(&g.pipe->dfull, g.dparity);
     g.dparity ^= 1u;
     fence_after_sync();
-    if (blockIdx.x == 0 && threadIdx.x == 0 && g_dbg_ts[62] < 8) g_dbg_ts[17 + 3 * g_dbg_ts[62]] = clock64();
 #pragma unroll
     for (int n0 = 0; n0 < NP; n0 += 16) {
         float d[16];
@@ -116,7 +113,6 @@ __device__ __forceinline__ void get_tile(Grp& g, Epi&& epi) {
         wait_ld();
         epi(n0, d);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && g_dbg_ts[62] < 8) { g_dbg_ts[18 + 3 * g_dbg_ts[62]] = clock64(); g_dbg_ts[62] += 1; }
     // the next put_chunk's fence::before_thread_sync + counter increment orders these reads before D is overwritten
 }
 template <int KP, int NP, class Loader, class Epi>
@@ -466,8 +462,6 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
 // ===================================================================================================
 // tc_s1_kernel: fused stride-1 ShuffleV2 block (reference shufflenetv2.py:19-32,48-51).
 // ===================================================================================================
-#define DBG_TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg_ts[i] = clock64(); } while (0)
-
 struct S1Args {
     Planes P;
     ChanTab tin, tout;
@@ -508,7 +502,6 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
         const int n = item / p.bandsPerImg;
         const int r0 = (item - n * p.bandsPerImg) * p.TR;
         const int rows = min(p.TR, H - r0);
-        if (item == blockIdx.x) DBG_TS(0);
         __syncthreads();
         // only the padding of T needs zeros: the two pad columns of every row and whole out-of-image halo rows
         for (int i = threadIdx.x; i < K * (rows + 2); i += G * 128) {
@@ -529,10 +522,8 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
             const float* ibase = p.P.base + (long long)n * p.P.sN + p.P.org + gr * p.P.Ws + x;
             float* tpos = T + (gr - (r0 - 1)) * WS + 1 + x;
             float v[KP];
-            if (item == blockIdx.x) DBG_TS(1);
 #pragma unroll
             for (int k = 0; k < KP; ++k) v[k] = valid ? __ldg(ibase + p.tin.c[k] * sC) : 0.f;    // all loads in flight at once
-            if (item == blockIdx.x) { float acc = 0.f; for (int k = 0; k < KP; ++k) acc += v[k]; if (acc == 123.456f) g_dbg_ts[63] = 1; DBG_TS(2); }
             pw_tile<KP, NP>(g, b1_hi, b1_lo,
                 [&](int k0, float (&a)[8]) {
 #pragma unroll
@@ -546,9 +537,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
                     }
                 });
         }
-        if (item == blockIdx.x) DBG_TS(3);
         __syncthreads();
-        if (item == blockIdx.x) DBG_TS(4);
         // ---- phase C: dw3x3 + BN -> pw2 + BN + ReLU -> output planes -------------------------------------------
         const int npix = rows * W;
         for (int tile = grp; tile * 128 < npix; tile += G) {
@@ -567,11 +556,8 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
                     }
                 });
         }
-        if (item == blockIdx.x) DBG_TS(5);
     }
-    DBG_TS(6);
     cta_teardown(&tmem_slot);
-    DBG_TS(7);
 }
 
 // ===================================================================================================
@@ -719,18 +705,19 @@ tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
     constexpr int G = 4, KP = 32, NP = 32, COLS = kACols + NP;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
-    __shared__ __align__(8) uint64_t xbar;
+    __shared__ __align__(8) uint64_t xbar[2];
     __shared__ uint32_t tmem_slot;
     const int TRo = p.TRo, TWo = p.TWo;
     const int IR = 4 * TRo + 3, Wst = 4 * TWo + 8;           // staged input rows / columns (column 0 <-> input column 4*ox0 - 4)
     const int CR = 2 * TRo + 1, CC = 2 * TWo + 1;            // conv tile
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     float* sB = smem;
-    float* Xin = sB + WFL;                                   // [3][IR][Wst]
-    float* Cv = Xin + 3 * IR * Wst;                          // [24][CR*CC]
+    float* XinBuf = sB + WFL;                                // 2 x [3][IR][Wst]: the next item's patch is staged while this one computes
+    const int xsz = 3 * IR * Wst;
+    float* Cv = XinBuf + 2 * xsz;                            // [24][CR*CC]
     copy_f4(sB, p.wpack, WFL, 512);
     publish_smem();
-    if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
+    if (threadIdx.x == 0) { mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1); fence_mbar_init(); }
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const float* scale = sB + 2 * NP * KP;
@@ -738,37 +725,32 @@ tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
     const int H = p.H, W = p.W, HC = H / 2, WC = W / 2, HO = H / 4, WO = W / 4;
     const int items = p.N * p.tilesX * p.tilesY;
     const int grp = threadIdx.x >> 7;
-    uint32_t xparity = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+
+    // stage the input patch of `item` into buffer `b` (bulk copies for fp32, converting loads for uint8)
+    auto stage = [&](int item, int b) {
         const int n = item / (p.tilesX * p.tilesY);
         const int rem = item - n * (p.tilesX * p.tilesY);
         const int ty = rem / p.tilesX, tx = rem - ty * p.tilesX;
-        const int oy0 = ty * TRo, ox0 = tx * TWo;
-        const int iy0 = 4 * oy0 - 3, ic0 = 4 * ox0 - 4;       // input row / column of staged (0,0)
-        const int c_lo = max(ic0, 0), c_hi = min(ic0 + Wst, W);   // valid input columns [c_lo, c_hi), multiples of 4
-        __syncthreads();
-        publish_smem();
-        // ---- stage the input patch -----------------------------------------------------------------------------------
+        const int iy0 = 4 * (ty * TRo) - 3, ic0 = 4 * (tx * TWo) - 4;
+        const int c_lo = max(ic0, 0), c_hi = min(ic0 + Wst, W);
+        float* Xin = XinBuf + b * xsz;
         if (!U8) {
             int nvalid = 0;
             for (int r = 0; r < IR; ++r) nvalid += (iy0 + r >= 0 && iy0 + r < H);
-            if (threadIdx.x == 0) mbar_expect_tx(&xbar, (uint32_t)(3 * nvalid * (c_hi - c_lo) * sizeof(float)));
+            if (threadIdx.x == 0) mbar_expect_tx(&xbar[b], (uint32_t)(3 * nvalid * (c_hi - c_lo) * sizeof(float)));
             for (int i = threadIdx.x; i < 3 * IR; i += 512) {
                 const int c = i / IR, r = i - c * IR;
                 const int iy = iy0 + r;
                 float* dst = Xin + (c * IR + r) * Wst;
                 if (iy >= 0 && iy < H) {
                     bulk_g2s(dst + (c_lo - ic0), reinterpret_cast<const float*>(p.x) + (((size_t)n * 3 + c) * H + iy) * W + c_lo,
-                             (uint32_t)((c_hi - c_lo) * sizeof(float)), &xbar);
+                             (uint32_t)((c_hi - c_lo) * sizeof(float)), &xbar[b]);
                     for (int j = 0; j < c_lo - ic0; ++j) dst[j] = 0.f;
                     for (int j = c_hi - ic0; j < Wst; ++j) dst[j] = 0.f;
                 } else {
                     for (int j = 0; j < Wst; ++j) dst[j] = 0.f;
                 }
             }
-            __syncthreads();
-            mbar_wait(&xbar, xparity);
-            xparity ^= 1u;
         } else {
             const int q4 = Wst / 4;
             for (int i = threadIdx.x; i < 3 * IR * q4; i += 512) {
@@ -782,8 +764,24 @@ tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
                 }
                 *reinterpret_cast<float4*>(Xin + cr * Wst + 4 * j4) = v;
             }
-            __syncthreads();
         }
+    };
+
+    uint32_t xpar[2] = {0u, 0u};
+    int it = 0;
+    if (blockIdx.x < items) stage(blockIdx.x, 0);
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const int n = item / (p.tilesX * p.tilesY);
+        const int rem = item - n * (p.tilesX * p.tilesY);
+        const int ty = rem / p.tilesX, tx = rem - ty * p.tilesX;
+        const int oy0 = ty * TRo, ox0 = tx * TWo;
+        const float* Xin = XinBuf + cur * xsz;
+        // the other buffer was last read by the conv phase of the previous item, which every thread left before the
+        // pooling barrier of that item: it is free, prefetch the next item into it
+        if (item + gridDim.x < items) { publish_smem(); stage(item + gridDim.x, cur ^ 1); }
+        if (!U8) { mbar_wait(&xbar[cur], xpar[cur]); xpar[cur] ^= 1u; }
+        __syncthreads();                                      // edge zero-fill / uint8 conversion stores of this buffer are visible
         // ---- conv as GEMM: thread = conv position -----------------------------------------------------------------
         const int npos = CR * CC;
         for (int tile = grp; tile * 128 < npos; tile += G) {
@@ -794,12 +792,20 @@ tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
             const bool valid = inb && cy >= 0 && cy < HC && cx >= 0 && cx < WC;
             const float* xp = Xin + (2 * lr) * Wst + 2 * lc + 1;
             float v[KP];
+            {
+                const float* rp = xp;
+                const int cstep = (IR - 3) * Wst;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+                for (int c = 0; c < 3; ++c) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+                    for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = valid ? xp[(c * IR + ky) * Wst + kx] : 0.f;
+                        for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = valid ? rp[kx] : 0.f;
+                        rp += Wst;
+                    }
+                    rp += cstep;
+                }
+            }
 #pragma unroll
             for (int k = 27; k < KP; ++k) v[k] = 0.f;
             pw_tile<KP, NP>(g, b_hi, b_lo,
@@ -818,17 +824,22 @@ tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
         __syncthreads();
         // ---- maxpool 3x3 s2 p1 (PyTorch pads with -inf) -> framed output planes ----------------------------------------
         const int rows = min(TRo, HO - oy0), cols = min(TWo, WO - ox0);
-        for (int i = threadIdx.x; i < 24 * rows * cols; i += 512) {
-            const int ch = i / (rows * cols);
-            const int r2 = i - ch * (rows * cols);
-            const int oyl = r2 / cols, oxl = r2 - oyl * cols;
-            const float* cv = Cv + ch * npos + (2 * oyl) * CC + 2 * oxl;
-            float m = cv[0];
-            m = fmaxf(m, cv[1]); m = fmaxf(m, cv[2]);
-            m = fmaxf(m, cv[CC]); m = fmaxf(m, cv[CC + 1]); m = fmaxf(m, cv[CC + 2]);
-            m = fmaxf(m, cv[2 * CC]); m = fmaxf(m, cv[2 * CC + 1]); m = fmaxf(m, cv[2 * CC + 2]);
-            plane_ptr(p.out, n, ch)[p.out.org + (oy0 + oyl) * p.out.Ws + ox0 + oxl] = m;
+        {   // warp <-> channel, lane <-> pooled pixel: no integer division in the hot loop
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int ch = warp; ch < 24; ch += 16) {
+                float* op = plane_ptr(p.out, n, ch) + p.out.org + oy0 * p.out.Ws + ox0;
+                const float* cbase = Cv + ch * npos;
+                for (int oyl = 0; oyl < rows; ++oyl)
+                    for (int oxl = lane; oxl < cols; oxl += 32) {
+                        const float* cv = cbase + (2 * oyl) * CC + 2 * oxl;
+                        float m = fmaxf(fmaxf(cv[0], cv[1]), cv[2]);
+                        m = fmaxf(m, fmaxf(fmaxf(cv[CC], cv[CC + 1]), cv[CC + 2]));
+                        m = fmaxf(m, fmaxf(fmaxf(cv[2 * CC], cv[2 * CC + 1]), cv[2 * CC + 2]));
+                        op[oyl * p.out.Ws + oxl] = m;
+                    }
+            }
         }
+        __syncthreads();                                      // Cv is rewritten by the next item's conv phase
     }
     cta_teardown(&tmem_slot);
 }
@@ -852,9 +863,9 @@ int tc_launch_stem(const void* x, int is_u8, const Planes& out, const float* wpa
     const int HO = H / 4, WO = W / 4;
     a.TRo = HO >= 2 ? 2 : 1;
     a.TWo = WO < 44 ? WO : 44;
-    while (a.TWo > 4 && (size_t)(2 * 32 * 32 + 64 + 3 * (4 * a.TRo + 3) * (4 * a.TWo + 8) + 24 * (2 * a.TRo + 1) * (2 * a.TWo + 1)) * sizeof(float) > 100 * 1024) --a.TWo;
+    while (a.TWo > 4 && (size_t)(2 * 32 * 32 + 64 + 2 * 3 * (4 * a.TRo + 3) * (4 * a.TWo + 8) + 24 * (2 * a.TRo + 1) * (2 * a.TWo + 1)) * sizeof(float) > 110 * 1024) --a.TWo;
     a.tilesX = (WO + a.TWo - 1) / a.TWo; a.tilesY = (HO + a.TRo - 1) / a.TRo;
-    const size_t bytes = (size_t)(2 * 32 * 32 + 64 + 3 * (4 * a.TRo + 3) * (4 * a.TWo + 8) + 24 * (2 * a.TRo + 1) * (2 * a.TWo + 1) + 4) * sizeof(float);
+    const size_t bytes = (size_t)(2 * 32 * 32 + 64 + 2 * 3 * (4 * a.TRo + 3) * (4 * a.TWo + 8) + 24 * (2 * a.TRo + 1) * (2 * a.TWo + 1) + 4) * sizeof(float);
     const int items = N * a.tilesX * a.tilesY;
     if (is_u8) {
         TRYL(set_smem_attr(tc_stem_kernel<true>, bytes));
@@ -1003,8 +1014,3 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
 }
 
 }  // namespace yfv2
-
-extern "C" __attribute__((visibility("default"))) int yfv2_debug_timestamps(long long* host64, int reset) {
-    if (reset) { long long z[64] = {0}; cudaMemcpyToSymbol(yfv2::g_dbg_ts, z, sizeof(z)); return 0; }
-    return cudaMemcpyFromSymbol(host64, yfv2::g_dbg_ts, 64 * sizeof(long long)) == cudaSuccess ? 0 : -2;
-}
