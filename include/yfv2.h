@@ -89,6 +89,11 @@ YFV2_API int yfv2_forward_u8(yfv2_plan* plan, const uint8_t* x, const void* pack
 YFV2_API int yfv2_decode(const float* const preds[6], int N, int H, int W, int A, int C,
                 const double* anchors_host, float* out, void* stream);
 
+/* ---- export_onnx head (model/detector.py:33-44): sigmoid(reg) | sigmoid(obj) | softmax(cls), channel-last --------------
+ * out2: [N, H/16, W/16, 5A+C], out3: [N, H/32, W/32, 5A+C] (what Detector(..., export_onnx=True).forward returns). */
+YFV2_API int yfv2_export_heads(const float* const preds[6], int N, int H, int W, int A, int C, float* out2, float* out3,
+                               void* stream);
+
 /* ---- non_max_suppression (utils/utils.py:232-296) + torchvision.ops.nms ------------------------------
  * dets: [N,M,5+C].  out: [N,max_det,6] rows (x1,y1,x2,y2,conf,cls) by descending conf; counts: [N];
  * kept_idx (optional, may be NULL): [N,max_det] row index into dets[n].  class_filter: n_filter device

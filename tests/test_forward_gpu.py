@@ -134,3 +134,15 @@ def test_every_fused_stage_against_reference_taps(golden_dir):
     np.testing.assert_allclose(plan.debug_gather(17).cpu().numpy(), g["tap_S2"], **TOL)
     for i, p in enumerate(preds):
         np.testing.assert_allclose(p.cpu().numpy(), g["pred%d" % i], **TOL)
+
+
+def test_export_onnx_head(golden_dir):
+    """Detector(..., export_onnx=True): sigmoid(reg) | sigmoid(obj) | softmax(cls), channel-last (model/detector.py:33-44)."""
+    import model.detector as det
+    g = dict(np.load(os.path.join(golden_dir, "net_small.npz")))
+    m = det.Detector(80, 3, True, True)
+    m.load_state_dict(synth.make_state_dict(11))
+    e2, e3 = m.cuda().eval()(synth.make_images(12, 2, 64, 96).cuda())
+    assert e2.shape == g["export_2"].shape and e3.shape == g["export_3"].shape
+    np.testing.assert_allclose(e2.cpu().numpy(), g["export_2"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(e3.cpu().numpy(), g["export_3"], rtol=1e-4, atol=1e-5)

@@ -150,6 +150,49 @@ decode_kernel(PostGeom g, float* __restrict__ out, int chunks0) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// export_onnx head (reference model/detector.py:33-44): sigmoid(reg) | sigmoid(obj) | softmax(cls) concatenated channel-last,
+// one [N,h,w,5A+C] tensor per level — the wire format the ncnn sample consumes.  grid (chunks per image, N).
+__global__ void __launch_bounds__(NT)
+export_head_kernel(PostGeom g, float* __restrict__ out2, float* __restrict__ out3, int chunks0) {
+    __shared__ float S[(5 * kMaxA + 32 * kCPL) * kSStride];
+    const int n = blockIdx.y;
+    const int lv = blockIdx.x < chunks0 ? 0 : 1;
+    const int cell0 = (lv ? blockIdx.x - chunks0 : blockIdx.x) * kChunkCells;
+    const int ncell = min(kChunkCells, g.hw[lv] - cell0);
+    stage_cells(S, g, n, lv, cell0, ncell);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int A = g.A, C = g.C, D = 5 * A + C;
+    float* out = lv ? out3 : out2;
+    for (int cl = warp; cl < ncell; cl += NT / 32) {
+        float* o = out + ((long long)n * g.hw[lv] + cell0 + cl) * D;
+        for (int ch = lane; ch < 5 * A; ch += 32) o[ch] = sigmoid_rn(S[ch * kSStride + cl]);
+        float l[kCPL];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kCPL; ++j) {
+            const int c = lane + 32 * j;
+            l[j] = (c < C) ? S[(5 * A + c) * kSStride + cl] : -INFINITY;
+            m = fmaxf(m, l[j]);
+        }
+        m = warp_max(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kCPL; ++j) {
+            const int c = lane + 32 * j;
+            l[j] = (c < C) ? expf(__fsub_rn(l[j], m)) : 0.f;
+            sum = __fadd_rn(sum, l[j]);
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int j = 0; j < kCPL; ++j) {
+            const int c = lane + 32 * j;
+            if (c < C) o[5 * A + c] = __fdiv_rn(l[j], sum);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // NMS
 struct NmsParams {
     float conf_thres;
@@ -488,6 +531,18 @@ extern "C" int yfv2_decode(const float* const preds[6], int N, int H, int W, int
     if (!out) { set_error("decode: null output"); return YFV2_EINVAL; }
     const int chunks0 = (g.hw[0] + kChunkCells - 1) / kChunkCells, chunks1 = (g.hw[1] + kChunkCells - 1) / kChunkCells;
     decode_kernel<<<dim3(chunks0 + chunks1, N), NT, 0, (cudaStream_t)stream>>>(g, out, chunks0);
+    YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}
+
+extern "C" int yfv2_export_heads(const float* const preds[6], int N, int H, int W, int A, int C, float* out2, float* out3, void* stream) {
+    PostGeom g;
+    const double dummy[4 * kMaxA] = {0};
+    int rc = fill_geom(g, preds, N, H, W, A, C, dummy);
+    if (rc) return rc;
+    if (!out2 || !out3) { set_error("export_heads: null output"); return YFV2_EINVAL; }
+    const int chunks0 = (g.hw[0] + kChunkCells - 1) / kChunkCells, chunks1 = (g.hw[1] + kChunkCells - 1) / kChunkCells;
+    export_head_kernel<<<dim3(chunks0 + chunks1, N), NT, 0, (cudaStream_t)stream>>>(g, out2, out3, chunks0);
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }

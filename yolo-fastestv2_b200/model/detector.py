@@ -67,11 +67,13 @@ class Detector(nn.Module):
                 raise NotImplementedError("export_onnx=True is an inference-only head")
             from model import train_ops
             return train_ops.forward_train(self, x.float() if x.dtype != torch.float32 else x)
-        if self.export_onnx:
-            raise NotImplementedError("export_onnx=True head (sigmoid/softmax + NHWC concat) is not part of this build yet")
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected input [N,3,H,W]")
         plan = self._plan_for(x)
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
-        return plan.forward(x)
+        preds = plan.forward(x)
+        if self.export_onnx:
+            print("export onnx ...")                      # the reference prints this on every export-mode forward
+            return yfv2_engine.export_heads(preds)
+        return preds

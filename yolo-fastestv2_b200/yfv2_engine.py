@@ -39,6 +39,8 @@ PROTOTYPES = {
                                        ctypes.c_void_p]),
     "yfv2_decode": (ctypes.c_int, [_c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                    ctypes.POINTER(ctypes.c_double), ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_export_heads": (ctypes.c_int, [_c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_nms_workspace_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "yfv2_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_double,
                                 ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
@@ -362,3 +364,17 @@ def op(name, tensors_and_ints, device):
             args.append(int(a))
     with torch.cuda.device(device):
         _check(getattr(lib(), "yfv2_op_" + name)(*args, _stream(device)), "op_" + name)
+
+
+def export_heads(preds):
+    """Detector(..., export_onnx=True) output: two channel-last [N,h,w,5A+C] tensors (sigmoid / sigmoid / softmax)."""
+    preds = [p.detach().contiguous().float() for p in preds]
+    N, _, h, w = preds[0].shape
+    A, C = preds[1].shape[1], preds[2].shape[1]
+    dev = preds[0].device
+    o2 = torch.empty((N, h, w, 5 * A + C), dtype=torch.float32, device=dev)
+    o3 = torch.empty((N, preds[3].shape[2], preds[3].shape[3], 5 * A + C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib().yfv2_export_heads(_ptr_array(preds), N, h * 16, w * 16, A, C, ctypes.c_void_p(o2.data_ptr()),
+                                       ctypes.c_void_p(o3.data_ptr()), _stream(dev)), "export_heads")
+    return o2, o3
