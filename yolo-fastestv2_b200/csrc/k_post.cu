@@ -342,8 +342,18 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             if (j < cn) {
                 const float4 bj = s.chbox[j];
                 const float aj = s.charea[j];
+                // four kept boxes per trip: the loads and IoU tests are independent, only the exit test is shared
                 bool dead = false;
-                for (int i = q; i < nk && !dead; i += NT / kNmsChunk) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
+                constexpr int STEP = NT / kNmsChunk;
+                int i = q;
+                for (; i + 3 * STEP < nk && !dead; i += 4 * STEP) {
+                    const bool d0 = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
+                    const bool d1 = iou_gt(s.kbox[i + STEP], s.karea[i + STEP], bj, aj, p);
+                    const bool d2 = iou_gt(s.kbox[i + 2 * STEP], s.karea[i + 2 * STEP], bj, aj, p);
+                    const bool d3 = iou_gt(s.kbox[i + 3 * STEP], s.karea[i + 3 * STEP], bj, aj, p);
+                    dead = d0 | d1 | d2 | d3;
+                }
+                for (; i < nk && !dead; i += STEP) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
                 if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
             }
         }
