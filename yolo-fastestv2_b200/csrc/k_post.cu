@@ -11,6 +11,7 @@
 // in fp32 compared as double against the threshold, stable descending order (ties by original row),
 // and no FMA contraction anywhere in that arithmetic — every step uses the __f*_rn intrinsics.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -440,9 +441,88 @@ nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
     sort_and_suppress(s, p, n);
 }
 
-// Fused: candidates come straight from the head logits (same device code as decode_kernel).
-__global__ void __launch_bounds__(NT)
-decode_nms_kernel(PostGeom g, NmsParams p) {
+// Fused: candidates come straight from the head logits.
+//
+// Fast path (C <= 80): ONE THREAD PER CELL instead of one warp per cell.  A thread keeps the C exponentials of its cell in
+// registers and reproduces the warp version's arithmetic bit for bit: the same expf arguments and the same summation tree
+// (32 partial sums of classes l, l+32, l+64, then the xor-butterfly levels 16,8,4,2,1), so the probabilities equal those
+// decode_kernel writes.  Per (cell, anchor) only the winning class needs the division and the product: conf_c =
+// fl(fl(e_c/sum)*obj) is monotone in e_c, so the maximum is attained at the first arg-max of e; classes whose e is within
+// 1e-5 of the maximum are re-checked exactly so the reference's "first index of the maximal product" rule still holds.
+// ~10x fewer warp instructions than warp-per-cell (the loads are coalesced across the 32 cells of a warp).
+constexpr int kCT = 80;
+
+__device__ __forceinline__ void thread_cell_candidates(const PostGeom& g, const NmsParams& p, const NmsSmem& s, int n, int lv, int cell,
+                                                       bool in_range, int row0) {
+    const int A = g.A, C = g.C, hw = g.hw[lv];
+    float e[kCT];
+    float sum = 1.f, emax = 0.f;
+    int cstar = 0;
+    if (in_range) {
+        const float* cp = g.cls[lv] + (long long)n * C * hw + cell;
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kCT; ++c) { e[c] = (c < C) ? __ldg(cp + (long long)c * hw) : -INFINITY; m = fmaxf(m, e[c]); }
+#pragma unroll
+        for (int c = 0; c < kCT; ++c) {
+            e[c] = (c < C) ? expf(__fsub_rn(e[c], m)) : 0.f;
+            if (e[c] > emax) { emax = e[c]; cstar = c; }             // first arg-max
+        }
+        float ps[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            float t = e[l];                                           // (0 + e_l) is exact
+            if (l + 32 < kCT) t = __fadd_rn(t, e[l + 32]);
+            if (l + 64 < kCT) t = __fadd_rn(t, e[l + 64]);
+            ps[l] = t;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < o; ++i) ps[i] = __fadd_rn(ps[i], ps[i + o]);
+        sum = ps[0];
+    }
+    const int y = cell / g.w[lv], x = cell - y * g.w[lv];
+    for (int a = 0; a < A; ++a) {
+        bool want = false;
+        float conf = 0.f, bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
+        int cls = 0;
+        if (in_range) {
+            const float obj = sigmoid_rn(__ldg(g.obj[lv] + ((long long)n * A + a) * hw + cell));
+            if (obj > p.conf_thres) {
+                conf = __fmul_rn(__fdiv_rn(emax, sum), obj);
+                cls = cstar;
+                const float near = emax * 0.99999f;
+                int nnear = 0;
+#pragma unroll
+                for (int c = 0; c < kCT; ++c) nnear += (e[c] >= near) ? 1 : 0;
+                if (nnear > 1) {                                      // rare: an earlier class may round to the same product
+                    bool found = false;
+#pragma unroll
+                    for (int c = 0; c < kCT; ++c)
+                        if (!found && c < cstar && e[c] >= near && __fmul_rn(__fdiv_rn(e[c], sum), obj) == conf) { cls = c; found = true; }
+                }
+                if (conf > p.conf_thres && class_ok(p, cls)) {
+                    want = true;
+                    const float* rp = g.reg[lv] + ((long long)n * 4 * A + 4 * a) * hw + cell;
+                    const float sx = sigmoid_rn(__ldg(rp)), sy = sigmoid_rn(__ldg(rp + hw));
+                    const float sw = sigmoid_rn(__ldg(rp + 2 * (long long)hw)), sh = sigmoid_rn(__ldg(rp + 3 * (long long)hw));
+                    const float st = g.stride[lv];
+                    bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), (float)x), st);
+                    by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), (float)y), st);
+                    const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+                    bw = (float)__dmul_rn((double)__fmul_rn(tw, tw), g.anc[lv][a][0]);
+                    bh = (float)__dmul_rn((double)__fmul_rn(th, th), g.anc[lv][a][1]);
+                }
+            }
+        }
+        const unsigned int slot = alloc_slots(s, want);
+        if (want) write_candidate(s, slot, bx, by, bw, bh, conf, cls, row0 + cell * A + a);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 2)
+decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
     float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
@@ -450,6 +530,19 @@ decode_nms_kernel(PostGeom g, NmsParams p) {
     if (threadIdx.x == 0) s.misc[0] = 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A = g.A, C = g.C;
+    if (fast) {
+        __syncthreads();
+        for (int lv = 0; lv < 2; ++lv) {
+            const int row0 = lv ? g.hw[0] * A : 0;
+            for (int c0 = 0; c0 < g.hw[lv]; c0 += NT) {
+                const int cell = c0 + threadIdx.x;
+                const bool in_range = cell < g.hw[lv];
+                thread_cell_candidates(g, p, s, n, lv, in_range ? cell : 0, in_range, row0);
+            }
+        }
+        sort_and_suppress(s, p, n);
+        return;
+    }
     for (int lv = 0; lv < 2; ++lv) {
         const int row0 = lv ? g.hw[0] * A : 0;
         for (int cell0 = 0; cell0 < g.hw[lv]; cell0 += kChunkCells) {
@@ -593,7 +686,7 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
     const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (size_t)(5 * A + C) * kSStride * sizeof(float);
     if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
     YFV2_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    decode_nms_kernel<<<N, NT, bytes, (cudaStream_t)stream>>>(g, p);
+    decode_nms_kernel<<<N, NT, bytes, (cudaStream_t)stream>>>(g, p, (C <= kCT && !getenv("YFV2_NMS_WARP_PER_CELL")) ? 1 : 0);
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }
