@@ -102,12 +102,13 @@ __device__ __forceinline__ void put_chunk(Grp& g, const float (&a)[8], int c, ui
 }
 // Collect the NP output columns of this thread's pixel.
 template <int NP, class Epi>
-__device__ __forceinline__ void get_tile(Grp& g, Epi&& epi) {
+__device__ __forceinline__ void get_tile(Grp& g, Epi&& epi, int ncols = NP) {
     mbar_wait(&g.pipe->dfull, g.dparity);
     g.dparity ^= 1u;
     fence_after_sync();
 #pragma unroll
     for (int n0 = 0; n0 < NP; n0 += 16) {
+        if (n0 >= ncols) break;                 // trailing all-padding column blocks (warp-uniform)
         float d[16];
         tmem_ld16(g.tlane + kACols + n0, d);
         wait_ld();
@@ -140,11 +141,11 @@ __device__ __forceinline__ void pw_tile_rolled(Grp& g, uint32_t b_hi, uint32_t b
 }
 
 // CTA prologue: TMEM allocation, barrier init.
-template <int G, int COLS>
+template <int G, int COLS, int TOT = kTmemCols>
 __device__ __forceinline__ Grp cta_setup(Pipe* pipes, uint32_t* tmem_slot) {
-    static_assert(G * COLS <= kTmemCols, "TMEM columns");
+    static_assert(G * COLS <= TOT, "TMEM columns");
     const int warp = threadIdx.x >> 5;
-    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 0) tmem_alloc(tmem_slot, TOT);
     if (threadIdx.x == 32) {
         for (int i = 0; i < G; ++i) {
             mbar_init(&pipes[i].empty[0], 1); mbar_init(&pipes[i].empty[1], 1);
@@ -165,10 +166,11 @@ __device__ __forceinline__ Grp cta_setup(Pipe* pipes, uint32_t* tmem_slot) {
     g.gtid = threadIdx.x & 127;
     return g;
 }
+template <int TOT = kTmemCols>
 __device__ __forceinline__ void cta_teardown(uint32_t* tmem_slot) {
     fence_before_sync();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, kTmemCols);
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(*tmem_slot, TOT);
 }
 template <int G>
 __device__ __forceinline__ void producers_sync() { __syncthreads(); }
@@ -195,16 +197,21 @@ __device__ __forceinline__ void copy_f4(float* dst, const float* __restrict__ sr
 // depthwise KSxKS (stride S) + BN (+ReLU) for 8 consecutive channels of one output pixel, from staged planes.
 //   win: top-left of the window in plane 0 of the staged buffer; wdw: per-channel [KS*KS taps, scale, shift, pad]
 template <int KS, int S, bool RELU>
+__device__ __forceinline__ void dw8p(const float* __restrict__ xk, int RS, int WS, const float* __restrict__ wk, bool valid, float (&a)[8]);
+template <int KS, int S, bool RELU>
 __device__ __forceinline__ void dw8(const float* __restrict__ win, int RS, int WS, const float* __restrict__ wdw, int k0, bool valid,
                                     float (&a)[8]) {
+    dw8p<KS, S, RELU>(win + k0 * RS, RS, WS, wdw + k0 * (KS == 3 ? 12 : 28), valid, a);
+}
+// same, given the window in the first of the 8 planes (xk, plane stride RS) and the first channel's weight row (wk)
+template <int KS, int S, bool RELU>
+__device__ __forceinline__ void dw8p(const float* __restrict__ xk, int RS, int WS, const float* __restrict__ wk, bool valid, float (&a)[8]) {
     constexpr int R = KS == 3 ? 12 : 28;
     if (!valid) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = 0.f;
         return;
     }
-    const float* xk = win + k0 * RS;
-    const float* wk = wdw + k0 * R;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float w[R];
@@ -312,27 +319,49 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
 }
 
 // ===================================================================================================
-// tc_dwpw_kernel: DW(KSxKS, stride S)+BN(+ReLU) -> PW(K->NP)+BN(+ReLU) -> planes, or (CHAIN) -> BN -> output conv
-// -> dense NCHW.  A work item is (image group, band of TR output rows, branch); the band (+halo) of the K source
-// planes of each image is staged in shared memory by bulk copies.
+// tc_dwpw_kernel: DW(KSxKS, stride S)+BN(+ReLU) -> PW(K->NP)+BN(+ReLU) -> planes, or (DENSE) -> dense NCHW prediction
+// tensors (the heads' second half: its pointwise, BN and the shared output conv are one folded matrix, see plan.cu).
+// A work item is (image group, band of TR output rows, branch); the band (+halo) of the K source planes of each image
+// is staged in shared memory by bulk copies.  Used by the stage-4 blocks and as the heads' fallback for maps of more
+// than 512 pixels (tc_head_kernel below is the fast path).
 // ===================================================================================================
 struct DwPwArgs {
     Planes in[2], out[2];      // per branch
     ChanTab tin[2], tout[2];
     const float* wdw[2];       // DW pack per branch
     const float* wpw[2];       // tc pack per branch
-    const float* wchain[2];    // chained output conv (tc pack, shift = bias), CHAIN only
-    float* dstA[2]; float* dstB[2]; int split[2]; int M[2];   // CHAIN: dense NCHW destinations
+    float* dstA[2]; float* dstB[2]; int split[2]; int M[2];   // DENSE: channels [0,split) -> dstA, [split,M) -> dstB
     int N, TR, bandsPerImg, nbranch, nout;
     int imgs;                  // images per work item (> 1 only when a band is a whole image)
 };
 
-template <int K, int NP, int G, int KS, int S, bool RELU_DW, bool RELU_OUT, bool CHAIN, int NP2>
+// epilogue of one 16-column block of a pixel's output row
+template <bool RELU_OUT, bool DENSE, bool IDENT = false>
+struct RowSink {
+    const float* scale; const float* shift;
+    float* obase; const unsigned short* tout; unsigned sCo; int nout;          // planes
+    float* dA; float* dB; int split, M; long long n, HW, opix;                  // dense
+    bool valid;
+    __device__ __forceinline__ void operator()(int n0, float (&d)[16]) const {
+        if (!valid) return;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int m = n0 + j;
+            float v = fmaf(d[j], scale[m], shift[m]);
+            if (RELU_OUT) v = fmaxf(v, 0.f);
+            if (!DENSE) { if (m < nout) obase[(IDENT ? (unsigned)m : (unsigned)tout[m]) * sCo] = v; }
+            else if (m < split) dA[(n * split + m) * HW + opix] = v;
+            else if (m < M) dB[(n * (M - split) + (m - split)) * HW + opix] = v;
+        }
+    }
+};
+
+template <int K, int NP, int G, int KS, int S, bool RELU_DW, bool RELU_OUT, bool DENSE>
 __global__ void __launch_bounds__(G * 128, 1)
 tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     constexpr int KP = K;
     static_assert(KP % 8 == 0 && NP % 16 == 0 && K <= G * 128, "shape");
-    constexpr int COLS = kACols + (CHAIN ? (NP > NP2 ? NP : NP2) : NP);
+    constexpr int COLS = kACols + NP;
     constexpr int PADK = KS / 2;
     constexpr int DWR = KS == 3 ? 12 : 28;
     extern __shared__ __align__(128) float smem[];
@@ -340,12 +369,10 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     __shared__ __align__(8) uint64_t xbar;
     __shared__ uint32_t tmem_slot;
     constexpr int WFL = 2 * NP * KP + 2 * NP;
-    constexpr int WFL2 = CHAIN ? 2 * NP2 * NP + 2 * NP2 : 0;
     float* sB = smem;                          // pw pack
-    float* sB2 = sB + WFL;                     // chained pack
-    float* sDW = sB2 + WFL2;                   // dw pack
+    float* sDW = sB + WFL;                     // dw pack
     float* X = sDW + K * DWR;                  // staged planes
-    const int Hout = p.out[0].H, Wout = p.out[0].W;
+    const int Hout = DENSE ? p.in[0].H : p.out[0].H, Wout = DENSE ? p.in[0].W : p.out[0].W;
     const int WS = p.in[0].Ws;
     const int RS1 = (S * (p.TR - 1) + KS) * WS;           // one image's band of one plane
     const int RS = RS1 * p.imgs;                           // plane stride of the staged buffer
@@ -353,10 +380,8 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
-    const uint32_t c_hi = smem_u32(sB2), c_lo = smem_u32(sB2 + NP2 * NP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
-    const float* bias2 = sB2 + 2 * NP2 * NP + NP2;
     const int ngroups = (p.N + p.imgs - 1) / p.imgs;       // image groups
     const int items = ngroups * p.bandsPerImg * p.nbranch;
     const int grp = threadIdx.x >> 7;
@@ -378,7 +403,6 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
             stage_bulk<K>(X + i * RS1, RS, p.in[br], p.tin[br], n0img + i, S * r0 + p.in[br].pad - PADK, nrows, &xbar, 0);
         if (br != loaded_branch) {
             copy_f4(sB, p.wpw[br], WFL, G * 128);
-            if (CHAIN) copy_f4(sB2, p.wchain[br], WFL2, G * 128);
             copy_f4(sDW, p.wdw[br], K * DWR, G * 128);
             loaded_branch = br;
             publish_smem();
@@ -388,7 +412,6 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
         xparity ^= 1u;
         const int ppi = rows * Wout;                        // pixels per image in this band
         const int npix = ppi * nimg;
-        const unsigned sCo = (unsigned)p.out[br].sC;
         for (int tile = grp; tile * 128 < npix; tile += G) {
             const int q = tile * 128 + g.gtid;
             const bool valid = q < npix;
@@ -397,66 +420,132 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
             const int n = n0img + im;
             const int orow = qi / Wout, ox = qi - orow * Wout;
             const float* win = X + im * RS1 + (S * orow) * WS + S * ox + coff;
-            if (!CHAIN) {
-                float* obase = p.out[br].base + (long long)n * p.out[br].sN + p.out[br].org + (r0 + orow) * p.out[br].Ws + ox;
-                pw_tile_rolled<KP, NP>(g, b_hi, b_lo,
-                    [&](int k0, float (&a)[8]) { dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a); },
-                    [&](int n0, float (&d)[16]) {
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int nn = n0 + j;
-                                if (nn < p.nout) {
-                                    float v = fmaf(d[j], scale[nn], shift[nn]);
-                                    if (RELU_OUT) v = fmaxf(v, 0.f);
-                                    obase[p.tout[br].c[nn] * sCo] = v;
-                                }
-                            }
-                        }
-                    });
+            RowSink<RELU_OUT, DENSE> sink;
+            sink.scale = scale; sink.shift = shift; sink.valid = valid;
+            if (!DENSE) {
+                sink.obase = p.out[br].base + (long long)n * p.out[br].sN + p.out[br].org + (r0 + orow) * p.out[br].Ws + ox;
+                sink.tout = p.tout[br].c; sink.sCo = (unsigned)p.out[br].sC; sink.nout = p.nout;
             } else {
-                // features (NP columns, p.nout real) -> BN -> second contraction against the output conv -> dense NCHW.
-#pragma unroll 1
-                for (int k0 = 0; k0 < KP; k0 += 8) {
-                    float a[8];
-                    dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a);
-                    put_chunk<KP, NP>(g, a, k0 >> 3, b_hi, b_lo);
-                }
-                float f[NP];
-                get_tile<NP>(g, [&](int n0, float (&d)[16]) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v = fmaf(d[j], scale[n0 + j], shift[n0 + j]);
-                        if (RELU_OUT) v = fmaxf(v, 0.f);
-                        f[n0 + j] = valid ? v : 0.f;
-                    }
-                });
-#pragma unroll
-                for (int k0 = 0; k0 < NP; k0 += 8) {
-                    float a[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = f[k0 + j];
-                    put_chunk<NP, NP2>(g, a, k0 / 8, c_hi, c_lo);
-                }
-                const int HW = Hout * Wout;
-                const long long opix = (long long)(r0 + orow) * Wout + ox;
-                const int split = p.split[br], M = p.M[br];
-                float* dA = p.dstA[br]; float* dB = p.dstB[br];
-                get_tile<NP2>(g, [&](int n0, float (&d)[16]) {
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int m = n0 + j;
-                            const float v = d[j] + bias2[m];
-                            if (m < split) dA[((long long)n * split + m) * HW + opix] = v;
-                            else if (m < M) dB[((long long)n * (M - split) + (m - split)) * HW + opix] = v;
-                        }
-                    }
-                });
+                sink.dA = p.dstA[br]; sink.dB = p.dstB[br]; sink.split = p.split[br]; sink.M = p.M[br];
+                sink.n = n; sink.HW = (long long)Hout * Wout; sink.opix = (long long)(r0 + orow) * Wout + ox;
             }
+            pw_tile_rolled<KP, NP>(g, b_hi, b_lo,
+                [&](int k0, float (&a)[8]) { dw8<KS, S, RELU_DW>(win, RS, WS, sDW, k0, valid, a); }, sink);
         }
     }
     cta_teardown(&tmem_slot);
+}
+
+// ===================================================================================================
+// tc_head_kernel: the detection heads' DW5x5+BN+ReLU -> PW, channel-streamed (reference fpn.py DWConvblock, detector.py
+// output convs).  One work item = (group of `imgs` whole images, branch) with at most G*128 pixels, one 128-pixel tile
+// per warpgroup, so the CTA never keeps more than 8 input channels of the item in shared memory: a dedicated producer
+// warp streams the framed planes of channels [8c, 8c+8) through a ring of kHeadBufs buffers with one bulk copy per
+// plane, the G warpgroups run the stencil on chunk c while chunks c+1.. are in flight and the tensor core contracts
+// chunk c-1.  Compared with tc_dwpw_kernel (whole 72-channel band resident) this needs ~1/9 of the staging memory, which
+// buys 16 compute warps per SM instead of 8 and whole-image tiles (no band halo re-reads, 95 % tile fill).
+// ===================================================================================================
+struct HeadArgs {
+    Planes in[2], out[2];      // per branch (ident channel tables)
+    const float* wdw[2];
+    const float* wpw[2];
+    float* dstA[2]; float* dstB[2]; int split[2]; int M[2];   // DENSE
+    int N, imgs, nout;
+};
+constexpr int kHeadBufs = 4;
+
+template <int K, int NP, int G, bool DENSE>
+__global__ void __launch_bounds__(G * 128 + 32, 1)
+tc_head_kernel(const __grid_constant__ HeadArgs p) {
+    constexpr int NCH = K / 8, NB = kHeadBufs, DWR = 28, COLS = 128, TOT = 512;
+    static_assert(K % 8 == 0 && NP % 16 == 0 && kACols + NP <= COLS && G * COLS <= TOT, "shape");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) Pipe pipes[G + 1];             // +1: the producer warp's (unused) slot
+    __shared__ __align__(8) uint64_t fullb[NB], freeb[NB];
+    __shared__ uint32_t tmem_slot;
+    constexpr int WFL = 2 * NP * K + 2 * NP;
+    float* sB = smem;
+    float* sDW = sB + WFL;
+    float* X = sDW + K * DWR;
+    const int H = p.in[0].H, W = p.in[0].W, WS = p.in[0].Ws;
+    const int PS = (H + 4) * WS;                            // one whole framed plane (frame of 2)
+    const int CS = PS * p.imgs;                             // channel stride inside a ring buffer
+    const int BUF = 8 * CS;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullb[i], 1); mbar_init(&freeb[i], G * 4); }
+        fence_mbar_init();
+    }
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (p.N + p.imgs - 1) / p.imgs;
+    const int items = 2 * ngroups;                          // branch-major: item t -> (branch t / ngroups, group t % ngroups)
+    uint32_t it = 0;                                        // chunks produced / consumed so far (same sequence on both sides)
+    if (warp == G * 4) {
+        // ---------------- producer warp ------------------------------------------------------------------------
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const uint32_t buf = it % NB, use = it / NB;
+                if (use > 0) mbar_wait(&freeb[buf], (use - 1) & 1u);     // all 4G compute warps are done reading this buffer
+                publish_smem();
+                if (lane == 0) mbar_expect_tx(&fullb[buf], (uint32_t)(8 * nimg * PS * sizeof(float)));
+                __syncwarp();
+                for (int j = lane; j < 8 * nimg; j += 32) {
+                    const int ch = j & 7, i = j >> 3;
+                    bulk_g2s(X + (size_t)buf * BUF + ch * CS + i * PS, plane_ptr(p.in[br], n0 + i, c * 8 + ch),
+                             (uint32_t)(PS * sizeof(float)), &fullb[buf]);
+                }
+            }
+        }
+    } else {
+        // ---------------- compute warpgroups ---------------------------------------------------------------------
+        const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * K);
+        const float* scale = sB + 2 * NP * K;
+        const float* shift = scale + NP;
+        const int grp = threadIdx.x >> 7;
+        const int HW = H * W;
+        int loaded_branch = -1;
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            if (br != loaded_branch) {
+                group_bar(1, G * 128);                      // every compute warp is done with the previous branch's weights
+                copy_f4(sB, p.wpw[br], WFL, G * 128);
+                copy_f4(sDW, p.wdw[br], K * DWR, G * 128);
+                publish_smem();
+                group_bar(1, G * 128);
+                loaded_branch = br;
+            }
+            const int q = grp * 128 + g.gtid;
+            const bool valid = q < HW * nimg;
+            const int im = valid ? q / HW : 0;
+            const int qi = valid ? q - im * HW : 0;
+            const int oy = qi / W, ox = qi - oy * W;
+            const int woff = im * PS + oy * WS + ox;        // window's top-left in the framed plane (frame 2 = the 5x5 halo)
+            RowSink<false, DENSE, true> sink;
+            sink.scale = scale; sink.shift = shift; sink.valid = valid;
+            if (!DENSE) {
+                sink.obase = p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox;
+                sink.tout = nullptr; sink.sCo = (unsigned)p.out[br].sC; sink.nout = p.nout;
+            } else {
+                sink.dA = p.dstA[br]; sink.dB = p.dstB[br]; sink.split = p.split[br]; sink.M = p.M[br];
+                sink.n = n0 + im; sink.HW = HW; sink.opix = qi;
+            }
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const uint32_t buf = it % NB;
+                mbar_wait(&fullb[buf], (it / NB) & 1u);
+                float a[8];
+                dw8p<5, 1, true>(X + (size_t)buf * BUF + woff, CS, WS, sDW + c * 8 * DWR, valid, a);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&freeb[buf]);
+                put_chunk<K, NP>(g, a, c, b_hi, b_lo);
+            }
+            get_tile<NP>(g, sink, DENSE ? p.M[br] : p.nout);
+        }
+    }
+    cta_teardown<TOT>(&tmem_slot);
 }
 
 // ===================================================================================================
@@ -976,14 +1065,50 @@ int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* t
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (stride == 1) return run(tc_dwpw_kernel<96, 96, G, 3, 1, false, true, false, 16>, 1);
-    return run(tc_dwpw_kernel<96, 96, G, 3, 2, false, true, false, 16>, 2);
+    if (stride == 1) return run(tc_dwpw_kernel<96, 96, G, 3, 1, false, true, false>, 1);
+    return run(tc_dwpw_kernel<96, 96, G, 3, 2, false, true, false>, 2);
 }
 
-// heads: half 0: T = BN(pw(ReLU(BN(dw5x5(S)))));  half 1: preds = outconv(BN(pw(ReLU(BN(dw5x5(T)))))) + bias.
-// branch 0 = cls head (outputs obj+cls), branch 1 = reg head.
+// heads: half 0: T = BN(pw(ReLU(BN(dw5x5(S)))));  half 1: preds = F(ReLU(BN(dw5x5(T)))) with F = outconv o BN o pw folded
+// into one [M x 72] matrix + bias at pack time (plan.cu).  branch 0 = cls head (outputs obj+cls), branch 1 = reg head.
 int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
-                    const float* wout_oc, const float* wout_reg, float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s) {
+                    float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s) {
+    if (A + C > 96 || 4 * A > 96) { set_error("tc heads: A+C=%d exceeds the output tile (96)", A + C); return YFV2_EUNSUPPORTED; }
+    if (sIn.pad != 2) { set_error("tc heads: the 5x5 stencil needs input planes framed by 2"); return YFV2_EINVAL; }
+    const int H = sIn.H, W = sIn.W;
+    const int np = half == 0 ? 80 : 96;
+    static const bool force_band = getenv("YFV2_HEADS_BAND") != nullptr;
+    // ---- fast path: channel-streamed whole-image items ----------------------------------------------------------
+    if (H * W <= 512 && !force_band) {
+        constexpr int G = 4;
+        HeadArgs a{};
+        a.N = N; a.nout = 72;
+        for (int b = 0; b < 2; ++b) { a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
+        if (half == 0) { a.in[0] = sIn; a.in[1] = sIn; a.out[0] = tcls; a.out[1] = treg; }
+        else {
+            a.in[0] = tcls; a.in[1] = treg;
+            a.dstA[0] = obj; a.dstB[0] = cls; a.split[0] = A; a.M[0] = A + C;
+            a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
+        }
+        const size_t PS = (size_t)(H + 4) * sIn.Ws;
+        const size_t wfl = (size_t)(2 * np * 72 + 2 * np) + 72 * 28;
+        a.imgs = 1;
+        while ((a.imgs + 1) * H * W <= G * 128 && a.imgs + 1 <= N &&
+               (wfl + kHeadBufs * 8 * PS * (a.imgs + 1) + 4) * sizeof(float) <= kSmemCap - 1024) ++a.imgs;
+        const size_t bytes = (wfl + kHeadBufs * 8 * PS * a.imgs + 4) * sizeof(float);
+        if (bytes <= kSmemCap - 1024) {
+            const int ngroups = (N + a.imgs - 1) / a.imgs;
+            auto run = [&](auto kern) -> int {
+                TRYL(set_smem_attr(kern, bytes));
+                kern<<<min(2 * ngroups, sm_count()), G * 128 + 32, bytes, s>>>(a);
+                YFV2_LAUNCH_CHECK();
+                return YFV2_OK;
+            };
+            if (half == 0) return run(tc_head_kernel<72, 80, G, false>);
+            return run(tc_head_kernel<72, 96, G, true>);
+        }
+    }
+    // ---- fallback: row bands of the whole 72-channel stack --------------------------------------------------------
     DwPwArgs a{};
     ChanTab ident;
     for (int i = 0; i < kMaxCh; ++i) ident.c[i] = (unsigned short)i;
@@ -992,16 +1117,13 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
     if (half == 0) { a.in[0] = sIn; a.in[1] = sIn; a.out[0] = tcls; a.out[1] = treg; }
     else {
         a.in[0] = tcls; a.in[1] = treg; a.out[0] = tcls; a.out[1] = treg;
-        a.wchain[0] = wout_oc; a.wchain[1] = wout_reg;
         a.dstA[0] = obj; a.dstB[0] = cls; a.split[0] = A; a.M[0] = A + C;
         a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
     }
-    const int Hout = sIn.H;
-    constexpr int NP = 80, NP2 = 96, G = 2;
-    if (A + C > NP2 || 4 * A > NP2) { set_error("tc heads: A+C=%d exceeds the chained tile (%d)", A + C, NP2); return YFV2_EUNSUPPORTED; }
-    auto run = [&](auto kern, bool chain) -> int {
-        const size_t wfl = (size_t)(2 * NP * 72 + 2 * NP) + (chain ? (size_t)(2 * NP2 * NP + 2 * NP2) : 0) + 72 * 28;
-        dwpw_geometry(a, Hout, wfl + 4, (size_t)72 * sIn.Ws, 5, 1, sIn.W, G);
+    constexpr int G = 2;
+    auto run = [&](auto kern) -> int {
+        const size_t wfl = (size_t)(2 * np * 72 + 2 * np) + 72 * 28;
+        dwpw_geometry(a, H, wfl + 4, (size_t)72 * sIn.Ws, 5, 1, W, G);
         const size_t bytes = (wfl + (size_t)72 * (a.TR + 4) * sIn.Ws * a.imgs + 4) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
         const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * 2;
@@ -1009,8 +1131,8 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (half == 0) return run(tc_dwpw_kernel<72, NP, G, 5, 1, true, false, false, 16>, false);
-    return run(tc_dwpw_kernel<72, NP, G, 5, 1, true, false, true, NP2>, true);
+    if (half == 0) return run(tc_dwpw_kernel<72, 80, G, 5, 1, true, false, false>);
+    return run(tc_dwpw_kernel<72, 96, G, 5, 1, true, false, true>);
 }
 
 }  // namespace yfv2

@@ -104,6 +104,40 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, int Nout, int K, int
     dst[NP * KP + o] = __uint_as_float(lo);
 }
 
+// Heads, second half (reference fpn.py DWConvblock tail + detector.py:17-19,35-41): pw(72->72), its BN and the shared output
+// conv are consecutive affine maps with no activation between them, so they are ONE matrix at inference time:
+//   F = Wout . diag(sc) . Wpw,   f = Wout . sh + bias          (products accumulated in fp64, rounded once to fp32)
+// rows [n_off, n_off+Mo) of the folded [96 x K] matrix Fw and of the bias Fb.
+__global__ void fold_head_kernel(const float* __restrict__ wout, const float* __restrict__ bout, int Mo, const float* __restrict__ wpw,
+                                 const float* gamma, const float* beta, const float* mean, const float* var, int K, int n_off,
+                                 float* __restrict__ Fw, float* __restrict__ Fb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Mo * K) {
+        const int m = i / K, k = i - m * K;
+        double acc = 0.0;
+        for (int j = 0; j < K; ++j) {
+            const float invstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[j], kBnEps)));
+            const float sc = __fmul_rn(invstd, gamma[j]);
+            acc += (double)wout[m * K + j] * (double)sc * (double)wpw[j * K + k];
+        }
+        Fw[(size_t)(n_off + m) * K + k] = (float)acc;
+    }
+    if (i < Mo) {
+        double acc = (double)bout[i];
+        for (int j = 0; j < K; ++j) {
+            const float invstd = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var[j], kBnEps)));
+            const float sc = __fmul_rn(invstd, gamma[j]);
+            const float sh = __fsub_rn(beta[j], __fmul_rn(mean[j], sc));
+            acc += (double)wout[i * K + j] * (double)sh;
+        }
+        Fb[n_off + i] = (float)acc;
+    }
+}
+__global__ void fold_affine_kernel(const float* __restrict__ Fb, int NP, float* __restrict__ aff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NP) { aff[i] = 1.0f; aff[NP + i] = Fb[i]; }
+}
+
 // dense NCHW copy of a logical tensor (tests / debugging only)
 __global__ void gather_kernel(Planes P, ChanTab tab, int Cn, float* __restrict__ out, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,6 +182,7 @@ struct yfv2_plan {
     int engine;                        // 0 = FFMA kernels (k_shuffle/k_fpn/k_head), 1 = tcgen05 kernels (k_tcnet)
     size_t tk_blk[kNumBlocks][3];      // tc packs per block: [0]=pw1 [1]=pw2 [2]=proj pw (stride-2 only)
     size_t tk_stem, tk_fpn3, tk_fpn2, tk_head[4][2], tk_out_oc, tk_out_reg;
+    size_t tk_fold[4], pk_foldw[4];    // heads' second pointwise + BN + output conv folded into one matrix (tc pack / fp32 scratch)
     ChanTab t96;                       // scratch plane ids for the K=96 blocks' pw1 output
     int n_stages;
     struct Stage { int kind, a, b; char name[24]; } stages[64];
@@ -273,6 +308,8 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     for (int i = 0; i < 4; ++i) for (int h = 0; h < 2; ++h) { p->tk_head[i][h] = pk; pk += align_up(2 * 80 * 72 + 160, 4); }
     p->tk_out_oc = pk; pk += align_up(2 * 96 * 80 + 192, 4);
     p->tk_out_reg = pk; pk += align_up(2 * 96 * 80 + 192, 4);
+    for (int i = 0; i < 4; ++i) { p->tk_fold[i] = pk; pk += align_up(2 * 96 * 72 + 192, 4); }
+    for (int i = 0; i < 4; ++i) { p->pk_foldw[i] = pk; pk += align_up(96 * 72 + 96, 4); }
     p->pk_floats = pk;
     for (int i = 0; i < 96; ++i) p->t96.c[i] = 0;   // filled per use (pool-specific offset)
 
@@ -402,6 +439,7 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
     TRY(pack_pw(cur, true, false, kFpnDepth, 288, pk + p->pk_fpn2, kFpnDepth, 0, s, TcDst{pk + p->tk_fpn2, 80, 288}));
     TRY(pack_pw(cur, true, false, kFpnDepth, 192, pk + p->pk_fpn3, kFpnDepth, 0, s, TcDst{pk + p->tk_fpn3, 80, 192}));
     const int head_order[4] = {0, 1, 3, 2};     // pk_head index: 0 cls2, 1 reg2, 2 cls3, 3 reg3
+    struct Pw2 { const float *w, *g, *b, *m, *v; } pw2[4];
     for (int i = 0; i < 4; ++i) {
         float* d = pk + p->pk_head[head_order[i]];
         const int dwn = dw5_pack_floats(kFpnDepth), pwn = pw_pack_floats(kFpnDepth, kFpnDepth);
@@ -409,16 +447,39 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
         TRY(pack_dw(cur, kFpnDepth, 5, d, s));
         TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + dwn, kFpnDepth, 0, s, TcDst{pk + p->tk_head[hi_][0], 80, 72}));
         TRY(pack_dw(cur, kFpnDepth, 5, d + dwn + pwn, s));
+        pw2[hi_] = Pw2{cur.params[cur.p], cur.params[cur.p + 1], cur.params[cur.p + 2], cur.bn[2 * cur.b], cur.bn[2 * cur.b + 1]};
         TRY(pack_pw(cur, true, false, kFpnDepth, kFpnDepth, d + 2 * dwn + pwn, kFpnDepth, 0, s, TcDst{pk + p->tk_head[hi_][1], 80, 72}));
     }
     // output_reg_layers, output_obj_layers, output_cls_layers (detector.py:17-19); obj and cls share one pack
     // the chained output convs contract over the 80-column (72 real) feature tile of the head's second pointwise
     const bool tc_ok = true;
+    const float* wo[3] = {cur.params[cur.p], cur.params[cur.p + 2], cur.params[cur.p + 4]};       // reg, obj, cls weights
+    const float* bo[3] = {cur.params[cur.p + 1], cur.params[cur.p + 3], cur.params[cur.p + 5]};   // and biases
     TRY(pack_pw(cur, false, true, 4 * p->A, kFpnDepth, pk + p->pk_out_reg, round4(4 * p->A), 0, s,
                 tc_ok ? TcDst{pk + p->tk_out_reg, 96, 80} : TcDst{nullptr, 0, 0}));
     const int Moc = round4(p->A + p->C);
     TRY(pack_pw(cur, false, true, p->A, kFpnDepth, pk + p->pk_out_oc, Moc, 0, s, tc_ok ? TcDst{pk + p->tk_out_oc, 96, 80} : TcDst{nullptr, 0, 0}));
     TRY(pack_pw(cur, false, true, p->C, kFpnDepth, pk + p->pk_out_oc, Moc, p->A, s, tc_ok ? TcDst{pk + p->tk_out_oc, 96, 80} : TcDst{nullptr, 0, 0}));
+    // folded second halves of the four heads (cls heads feed obj|cls, reg heads feed reg)
+    for (int h = 0; h < 4; ++h) {
+        const Pw2& q = pw2[h];
+        float* Fw = pk + p->pk_foldw[h];
+        float* Fb = Fw + 96 * kFpnDepth;
+        const int K = kFpnDepth;
+        auto fold = [&](int which, int Mo, int n_off) -> int {
+            if (!wo[which] || !bo[which]) { set_error("pack_weights: null output-layer tensor"); return YFV2_EINVAL; }
+            fold_head_kernel<<<(Mo * K + 255) / 256, 256, 0, s>>>(wo[which], bo[which], Mo, q.w, q.g, q.b, q.m, q.v, K, n_off, Fw, Fb);
+            YFV2_LAUNCH_CHECK();
+            return YFV2_OK;
+        };
+        if (h & 1) { TRY(fold(0, 4 * p->A, 0)); }
+        else { TRY(fold(1, p->A, 0)); TRY(fold(2, p->C, p->A)); }
+        float* dst = pk + p->tk_fold[h];
+        pack_tc_kernel<<<(96 * K + 255) / 256, 256, 0, s>>>(Fw, 96, K, 96, K, 0, dst);
+        YFV2_LAUNCH_CHECK();
+        fold_affine_kernel<<<1, 96, 0, s>>>(Fb, 96, dst + 2 * 96 * K);
+        YFV2_LAUNCH_CHECK();
+    }
     if (cur.p != YFV2_NUM_PARAMS || cur.b != YFV2_NUM_BN) {
         set_error("pack_weights: internal walk consumed %d params / %d BN layers", cur.p, cur.b);
         return YFV2_EINVAL;
@@ -437,7 +498,7 @@ int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, 
 int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
                      const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
 int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
-                    const float* wout_oc, const float* wout_reg, float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s);
+                    float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s);
 }
 
 namespace {
@@ -484,8 +545,9 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             // DW pack = first 72*28 floats of each half of the head pack
             const size_t half_off = (size_t)half * (dw5_pack_floats(kFpnDepth) + pw_pack_floats(kFpnDepth, kFpnDepth));
             const float* wdw[2] = {w_cls + half_off, w_reg + half_off};
-            const float* wpw[2] = {pk + p->tk_head[2 * lv][half], pk + p->tk_head[2 * lv + 1][half]};
-            TRY(tc_launch_heads(half, sIn, t_cls, t_reg, wdw, wpw, pk + p->tk_out_oc, pk + p->tk_out_reg, preds[3 * lv], preds[3 * lv + 1],
+            const float* wpw[2] = {half ? pk + p->tk_fold[2 * lv] : pk + p->tk_head[2 * lv][0],
+                                   half ? pk + p->tk_fold[2 * lv + 1] : pk + p->tk_head[2 * lv + 1][0]};
+            TRY(tc_launch_heads(half, sIn, t_cls, t_reg, wdw, wpw, preds[3 * lv], preds[3 * lv + 1],
                                 preds[3 * lv + 2], p->A, p->C, p->N, s));
         } break;
         case 10: {   // tc fused stride-1 block
