@@ -1,144 +1,235 @@
 // K0 — stem: conv3x3 s2 p1 (3->24, no bias) + BN + ReLU + maxpool3x3 s2 p1, one pass.
-// Reference: model/backbone/shufflenetv2.py:74-80,103-104.  Input NCHW fp32 (or uint8 with the
-// `/255.0` of utils/utils.py:368 fused into the load), output 24 planes at H/4 x W/4.
+// Reference: model/backbone/shufflenetv2.py:74-80,103-104.  Input NCHW fp32 (or uint8 with the `/255.0` of
+// utils/utils.py:368 fused into the load), output 24 framed planes at H/4 x W/4.
 //
-// One CTA = one 8x16 output tile of one image.  It stages the 35x67x3 input patch in shared memory,
-// produces the 17x33 conv positions the tile's pool windows touch (8 output channels per pass, three
-// passes), and max-pools straight out of shared memory.  Conv positions outside the conv output are
-// -inf so they never win a pool window (PyTorch pads max_pool2d with -inf).
+// Why CUDA cores and not tcgen05: the contraction is K = 27 taps, N = 24 channels.  As a 3xTF32 UMMA (k_tcnet.cu,
+// tc_stem_kernel, kept behind YFV2_STEM_TC) the operand split, the TMEM round trip and the smem epilogue cost ~900 warp
+// instructions per 32 conv positions against 648 FFMA for doing the products directly, and the producer/consumer chain
+// adds barriers on top (ncu: 546 M warp instructions, 60 % issue, 26 % barrier stalls, 800 us).  This kernel is a
+// register-tiled direct convolution: one thread = 4 adjacent conv positions of one conv row x all 24 channels
+// (96 accumulators), inputs come from three aligned LDS.128 per (channel, kernel row), weights from warp-uniform
+// LDS.128, i.e. 2592 FFMA against ~190 shared-memory instructions (93 % FFMA in the main loop).
+//
+// A work item is (image, band of TRo pooled rows, tile of TWo <= 44 pooled columns):
+//   0. the input patch arrives by one TMA bulk copy per (channel, row) [uint8: converting loads], prefetched while the
+//      previous item pools;
+//   1. conv + BN (scale folded into the weights, shift = accumulator init) for the CR = 2 TRo + 1 conv rows the pool
+//      windows touch; positions outside the conv output become -inf (PyTorch pads max_pool2d with -inf);
+//   2. horizontal 3-max in registers (the one column a thread lacks comes from its right neighbour through shared
+//      memory), vertical 3-max + ReLU from shared memory -> framed output planes.  ReLU commutes with max, so it runs
+//      once per pooled value instead of once per conv value.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace yfv2 {
 
 namespace {
-constexpr int OT_H = 8, OT_W = 16;               // output tile (stride-4 grid)
-constexpr int CT_H = 2 * OT_H + 1, CT_W = 2 * OT_W + 1;   // 17 x 33 conv positions
-constexpr int IT_H = 2 * CT_H + 1, IT_W = 2 * CT_W + 1;   // 35 x 67 input pixels
-constexpr int IT_WS = 67;                         // row stride (odd: conflict-free stride-2 reads)
-constexpr int NPOS = CT_H * CT_W;                 // 561
-constexpr int STEM_THREADS = 288;                 // 2 rounds cover 561 positions
-constexpr int CG = 8;                             // channels per pass
+using namespace tc;
+
+constexpr int ST_THREADS = 256;
+constexpr int kStemW = 27 * 24 + 24;              // folded weights [27][24] | shift[24]
+
+struct StemFArgs {
+    const void* x;
+    Planes out;
+    const float* wpack;     // [27][24] | scale[24] | shift[24]
+    int N, H, W;
+    int TRo, TWo, tilesX, tilesY, S;
+};
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 template <bool U8>
-__global__ void __launch_bounds__(STEM_THREADS)
-stem_kernel(const void* __restrict__ xin, Planes out, const float* __restrict__ wpack, int H, int W, int tilesX) {
-    __shared__ float s_in[3 * IT_H * IT_WS];
-    __shared__ float s_conv[CG * NPOS];
-    __shared__ __align__(16) float s_w[kStemPackFloats];
-
-    const int n = blockIdx.y;
-    const int ty = blockIdx.x / tilesX, tx = blockIdx.x % tilesX;
-    const int oy0 = ty * OT_H, ox0 = tx * OT_W;
-    const int cy0 = 2 * oy0 - 1, cx0 = 2 * ox0 - 1;
-    const int iy0 = 2 * cy0 - 1, ix0 = 2 * cx0 - 1;
-    const int HC = H / 2, WC = W / 2, HO = H / 4, WO = W / 4;
+__global__ void __launch_bounds__(ST_THREADS, 2)
+stem_kernel(const __grid_constant__ StemFArgs p) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t xbar;
+    const int TRo = p.TRo, TWo = p.TWo, S = p.S;
+    const int CR = 2 * TRo + 1, IR = 4 * TRo + 3, Wst = 4 * TWo + 12;     // staged column 0 <-> input column 4*ox0 - 4
+    const int HSW = 2 * S;
+    float* sW = smem;                                  // folded weights + shift
+    float* Xin = sW + kStemW;                          // [3][IR][Wst]
+    float* Hs = Xin + 3 * IR * Wst;                    // [24][CR][HSW] horizontal maxima; its head doubles as
+    float* E = Hs;                                     // [24][CR][S]   first conv column of every strip
     const int tid = threadIdx.x;
+    {   // BN scale folded into the weights (one rounding per weight), shift kept as the accumulator's start value
+        const float* scale = p.wpack + 27 * 24;
+        for (int i = tid; i < 27 * 24; i += ST_THREADS) sW[i] = __fmul_rn(__ldg(p.wpack + i), __ldg(scale + (i % 24)));
+        if (tid < 24) sW[27 * 24 + tid] = __ldg(scale + 24 + tid);
+    }
+    if (tid == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const int H = p.H, W = p.W, HC = H / 2, WC = W / 2, HO = H / 4, WO = W / 4;
+    const int items = p.N * p.tilesX * p.tilesY;
 
-    copy_to_smem(s_w, wpack, kStemPackFloats);
-    // input patch: fp32 goes through cp.async (all loads in flight at once); uint8 is converted on the fly
-    // in batches of 8 independent loads per thread
-    if (!U8) {
-        for (int i = tid; i < 3 * IT_H * IT_W; i += STEM_THREADS) {
-            const int c = i / (IT_H * IT_W);
-            const int rem = i - c * (IT_H * IT_W);
-            const int r = rem / IT_W, q = rem - r * IT_W;
-            const int iy = iy0 + r, ix = ix0 + q;
-            float* dst = &s_in[(c * IT_H + r) * IT_WS + q];
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                cp_async4(dst, reinterpret_cast<const float*>(xin) + ((((size_t)n * 3 + c) * H + iy) * W + ix));
-            else
-                *dst = 0.f;
-        }
-        cp_async_wait_all();
-    } else {
-        constexpr int TOT = 3 * IT_H * IT_W, UNR = 8;
-        for (int i0 = tid; i0 < TOT; i0 += STEM_THREADS * UNR) {
-            uint8_t v[UNR];
-            int sidx[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int i = i0 + u * STEM_THREADS;
-                v[u] = 0; sidx[u] = -1;
-                if (i < TOT) {
-                    const int c = i / (IT_H * IT_W);
-                    const int rem = i - c * (IT_H * IT_W);
-                    const int r = rem / IT_W, q = rem - r * IT_W;
-                    const int iy = iy0 + r, ix = ix0 + q;
-                    sidx[u] = (c * IT_H + r) * IT_WS + q;
-                    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                        v[u] = __ldg(reinterpret_cast<const uint8_t*>(xin) + ((((size_t)n * 3 + c) * H + iy) * W + ix));
+    auto stage = [&](int item) {
+        const int n = item / (p.tilesX * p.tilesY);
+        const int rem = item - n * (p.tilesX * p.tilesY);
+        const int ty = rem / p.tilesX, tx = rem - ty * p.tilesX;
+        const int iy0 = 4 * (ty * TRo) - 3, ic0 = 4 * (tx * TWo) - 4;
+        const int c_lo = max(ic0, 0), c_hi = min(ic0 + Wst, W);
+        if (!U8) {
+            const int r_lo = max(iy0, 0), r_hi = min(iy0 + IR, H);
+            if (tid == 0) mbar_expect_tx(&xbar, (uint32_t)(3 * (r_hi - r_lo) * (c_hi - c_lo) * sizeof(float)));
+            for (int i = tid; i < 3 * IR; i += ST_THREADS) {
+                const int c = i / IR, r = i - c * IR;
+                const int iy = iy0 + r;
+                float* dst = Xin + (c * IR + r) * Wst;
+                if (iy >= 0 && iy < H) {
+                    bulk_g2s(dst + (c_lo - ic0), reinterpret_cast<const float*>(p.x) + (((size_t)n * 3 + c) * H + iy) * W + c_lo,
+                             (uint32_t)((c_hi - c_lo) * sizeof(float)), &xbar);
+                    for (int j = 0; j < c_lo - ic0; ++j) dst[j] = 0.f;
+                    for (int j = c_hi - ic0; j < Wst; ++j) dst[j] = 0.f;
+                } else {
+                    for (int j = 0; j < Wst; ++j) dst[j] = 0.f;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (sidx[u] >= 0) s_in[sidx[u]] = __fdiv_rn((float)v[u], 255.0f);
+        } else {
+            const int q4 = Wst / 4;
+            for (int i = tid; i < 3 * IR * q4; i += ST_THREADS) {
+                const int cr = i / q4, j4 = i - cr * q4;
+                const int c = cr / IR, r = cr - c * IR;
+                const int iy = iy0 + r, ix = ic0 + 4 * j4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                    const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(p.x) + (((size_t)n * 3 + c) * H + iy) * W + ix));
+                    v = make_float4(__fdiv_rn((float)u.x, 255.0f), __fdiv_rn((float)u.y, 255.0f), __fdiv_rn((float)u.z, 255.0f), __fdiv_rn((float)u.w, 255.0f));
+                }
+                *reinterpret_cast<float4*>(Xin + cr * Wst + 4 * j4) = v;
+            }
         }
-    }
-    __syncthreads();
+    };
 
-    const float* s_scale = s_w + 27 * 24;
-    const float* s_shift = s_scale + 24;
+    const int r = tid / S, s = tid - r * S;                  // conv row of the band / strip of 4 conv columns
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t xpar = 0;
+    if (blockIdx.x < items) stage(blockIdx.x);
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = item / (p.tilesX * p.tilesY);
+        const int rem = item - n * (p.tilesX * p.tilesY);
+        const int ty = rem / p.tilesX, tx = rem - ty * p.tilesX;
+        const int oy0 = ty * TRo, ox0 = tx * TWo;
+        const int rows = min(TRo, HO - oy0), cols = min(TWo, WO - ox0);
+        const bool active = r < 2 * rows + 1;
+        if (!U8) { mbar_wait(&xbar, xpar); xpar ^= 1u; }
+        __syncthreads();                                      // B0: edge zero-fill / uint8 stores visible; Hs free again
 
-    for (int g = 0; g < 24 / CG; ++g) {
-        for (int pos = tid; pos < NPOS; pos += STEM_THREADS) {
-            const int ly = pos / CT_W, lx = pos - ly * CT_W;
-            const int cy = cy0 + ly, cx = cx0 + lx;
-            float res[CG];
-            if (cy >= 0 && cy < HC && cx >= 0 && cx < WC) {
-                float acc[CG];
+        // ---- 1. conv: acc[j][ch], j = position 4s+j of conv row r (tile-local) ----------------------------------------
+        float h0[24], h1[24];
+        if (active) {
+            float acc[4][24];
 #pragma unroll
-                for (int j = 0; j < CG; ++j) acc[j] = 0.f;
+            for (int ch = 0; ch < 24; ++ch) {
+                const float sh = sW[27 * 24 + ch];
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+                for (int j = 0; j < 4; ++j) acc[j][ch] = sh;
+            }
+            const float* xb = Xin + (2 * r) * Wst + 8 * s;   // staged col of (position j, tap kx) = 8s + 2j + kx + 1
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+            for (int c = 0; c < 3; ++c) {
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float v = s_in[(c * IT_H + 2 * ly + ky) * IT_WS + 2 * lx + kx];
-                            const float* wr = s_w + (c * 9 + ky * 3 + kx) * 24 + g * CG;
-                            const float4 w0 = *reinterpret_cast<const float4*>(wr);
-                            const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-                            acc[0] = fmaf(w0.x, v, acc[0]); acc[1] = fmaf(w0.y, v, acc[1]);
-                            acc[2] = fmaf(w0.z, v, acc[2]); acc[3] = fmaf(w0.w, v, acc[3]);
-                            acc[4] = fmaf(w1.x, v, acc[4]); acc[5] = fmaf(w1.y, v, acc[5]);
-                            acc[6] = fmaf(w1.z, v, acc[6]); acc[7] = fmaf(w1.w, v, acc[7]);
+                for (int ky = 0; ky < 3; ++ky) {
+                    float x[12];
+                    const float4* xr = reinterpret_cast<const float4*>(xb + (c * IR + ky) * Wst);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) { const float4 v = xr[t]; x[4 * t] = v.x; x[4 * t + 1] = v.y; x[4 * t + 2] = v.z; x[4 * t + 3] = v.w; }
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4* wr = reinterpret_cast<const float4*>(sW + ((c * 3 + ky) * 3 + kx) * 24);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) {
+                            const float4 w = wr[q];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float xv = x[2 * j + kx + 1];
+                                acc[j][4 * q] = fmaf(xv, w.x, acc[j][4 * q]);
+                                acc[j][4 * q + 1] = fmaf(xv, w.y, acc[j][4 * q + 1]);
+                                acc[j][4 * q + 2] = fmaf(xv, w.z, acc[j][4 * q + 2]);
+                                acc[j][4 * q + 3] = fmaf(xv, w.w, acc[j][4 * q + 3]);
+                            }
                         }
-#pragma unroll
-                for (int j = 0; j < CG; ++j)
-                    res[j] = fmaxf(fmaf(acc[j], s_scale[g * CG + j], s_shift[g * CG + j]), 0.f);
-            } else {
-#pragma unroll
-                for (int j = 0; j < CG; ++j) res[j] = -INFINITY;
+                    }
+                }
             }
+            // conv positions outside the conv output never win a pool window
+            const int cy = 2 * oy0 - 1 + r, cx = 2 * ox0 - 1 + 4 * s;
+            const bool rowok = cy >= 0 && cy < HC;
+            if (!rowok || cx < 0 || cx + 3 >= WC) {
 #pragma unroll
-            for (int j = 0; j < CG; ++j) s_conv[j * NPOS + pos] = res[j];
-        }
-        __syncthreads();
-        for (int i = tid; i < CG * OT_H * OT_W; i += STEM_THREADS) {
-            const int j = i / (OT_H * OT_W);
-            const int rem = i - j * (OT_H * OT_W);
-            const int oyl = rem / OT_W, oxl = rem - oyl * OT_W;
-            const int oy = oy0 + oyl, ox = ox0 + oxl;
-            if (oy < HO && ox < WO) {
-                const float* cv = s_conv + j * NPOS + (2 * oyl) * CT_W + 2 * oxl;
-                float m = cv[0];
-                m = fmaxf(m, cv[1]); m = fmaxf(m, cv[2]);
-                m = fmaxf(m, cv[CT_W]); m = fmaxf(m, cv[CT_W + 1]); m = fmaxf(m, cv[CT_W + 2]);
-                m = fmaxf(m, cv[2 * CT_W]); m = fmaxf(m, cv[2 * CT_W + 1]); m = fmaxf(m, cv[2 * CT_W + 2]);
-                plane_ptr(out, n, g * CG + j)[out.org + oy * out.Ws + ox] = m;
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = rowok && cx + j >= 0 && cx + j < WC;
+                    if (!ok) {
+#pragma unroll
+                        for (int ch = 0; ch < 24; ++ch) acc[j][ch] = -INFINITY;
+                    }
+                }
+            }
+            // horizontal 3-max, part 1: pooled column 2s <- positions 0,1,2; 2s+1 <- positions 2,3 (+ the neighbour's 0 below)
+#pragma unroll
+            for (int ch = 0; ch < 24; ++ch) {
+                E[(ch * CR + r) * S + s] = acc[0][ch];
+                h0[ch] = max3(acc[0][ch], acc[1][ch], acc[2][ch]);
+                h1[ch] = fmaxf(acc[2][ch], acc[3][ch]);
             }
         }
-        __syncthreads();
+        __syncthreads();                                      // B1: every read of Xin is done, E is visible
+        if (item + gridDim.x < items) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of Xin before the async-proxy refill
+            stage(item + gridDim.x);                          // overlaps the pooling below
+        }
+        if (active && s + 1 < S) {
+#pragma unroll
+            for (int ch = 0; ch < 24; ++ch) h1[ch] = fmaxf(h1[ch], E[(ch * CR + r) * S + s + 1]);
+        }
+        __syncthreads();                                      // B2: E has been read, Hs may overwrite it
+        if (active) {
+#pragma unroll
+            for (int ch = 0; ch < 24; ++ch)
+                *reinterpret_cast<float2*>(Hs + (ch * CR + r) * HSW + 2 * s) = make_float2(h0[ch], h1[ch]);
+        }
+        __syncthreads();                                      // B3
+        // ---- 3. vertical 3-max + ReLU -> output planes: warp <-> (channel, pooled row), lane <-> pooled column ------------
+        for (int pr = warp; pr < 24 * rows; pr += ST_THREADS / 32) {
+            const int ch = pr / rows, oyl = pr - ch * rows;
+            const float* hb = Hs + (ch * CR + 2 * oyl) * HSW;
+            float* op = plane_ptr(p.out, n, ch) + p.out.org + (oy0 + oyl) * p.out.Ws + ox0;
+            for (int pc = lane; pc < cols; pc += 32)
+                op[pc] = fmaxf(max3(hb[pc], hb[HSW + pc], hb[2 * HSW + pc]), 0.f);
+        }
     }
+}
+
+__host__ size_t stem_smem_bytes(int TRo, int TWo, int S) {
+    const int CR = 2 * TRo + 1, IR = 4 * TRo + 3, Wst = 4 * TWo + 12;
+    return (size_t)(kStemW + 3 * IR * Wst + 24 * CR * 2 * S + 4) * sizeof(float);
 }
 }  // namespace
 
 int launch_stem(const StemArgs& a, cudaStream_t s) {
+    if (a.H % 4 || a.W % 4 || a.H < 4 || a.W < 4) { set_error("stem: input %dx%d must be a multiple of 4", a.H, a.W); return YFV2_EINVAL; }
+    StemFArgs k{a.x, a.out, a.wpack, a.N, a.H, a.W, 0, 0, 0, 0, 0};
     const int HO = a.H / 4, WO = a.W / 4;
-    const int tilesX = (WO + OT_W - 1) / OT_W, tilesY = (HO + OT_H - 1) / OT_H;
-    dim3 grid(tilesX * tilesY, a.N);
-    if (a.is_u8) stem_kernel<true><<<grid, STEM_THREADS, 0, s>>>(a.x, a.out, a.wpack, a.H, a.W, tilesX);
-    else         stem_kernel<false><<<grid, STEM_THREADS, 0, s>>>(a.x, a.out, a.wpack, a.H, a.W, tilesX);
+    // tiles of at most 44 pooled columns, as equal as possible; S strips of 4 conv columns cover the 2 TWo + 1 conv columns
+    k.tilesX = (WO + 43) / 44;
+    k.TWo = (WO + k.tilesX - 1) / k.tilesX;
+    k.S = (2 * k.TWo + 1 + 3) / 4;
+    // as many conv rows as the 256 threads cover, within ~half an SM's shared memory (two CTAs per SM)
+    k.TRo = (ST_THREADS / k.S - 1) / 2;
+    if (k.TRo > HO) k.TRo = HO;
+    while (k.TRo > 1 && stem_smem_bytes(k.TRo, k.TWo, k.S) > 112 * 1024) --k.TRo;
+    if (k.TRo < 1) k.TRo = 1;
+    const size_t bytes = stem_smem_bytes(k.TRo, k.TWo, k.S);
+    if ((2 * k.TRo + 1) * k.S > ST_THREADS || bytes > kSmemCap - 1024) { set_error("stem: unsupported geometry %dx%d", a.H, a.W); return YFV2_EUNSUPPORTED; }
+    k.tilesY = (HO + k.TRo - 1) / k.TRo;
+    const int items = a.N * k.tilesX * k.tilesY;
+    const int grid = items < 2 * sm_count() ? items : 2 * sm_count();
+    if (a.is_u8) {
+        YFV2_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        stem_kernel<true><<<grid, ST_THREADS, bytes, s>>>(k);
+    } else {
+        YFV2_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        stem_kernel<false><<<grid, ST_THREADS, bytes, s>>>(k);
+    }
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }

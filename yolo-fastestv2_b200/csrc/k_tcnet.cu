@@ -253,12 +253,13 @@ struct PwArgs {
 };
 
 template <int KA, int KB, int SHA, int NP, int G, bool RELU>
-__global__ void __launch_bounds__(G * 128, 2)
+__global__ void __launch_bounds__(G * 128, (G * (kACols + NP) > kTmemCols) ? 1 : 2)
 tc_pw_kernel(const __grid_constant__ PwArgs p) {
     constexpr int KP = KA + KB;
     constexpr int PF = 48;                                   // channels prefetched per batch of global loads
     static_assert(KP % PF == 0 && NP % 16 == 0, "shape");
     constexpr int COLS = kACols + NP;
+    constexpr int TOT = (G * COLS > kTmemCols) ? 512 : kTmemCols;   // 4 groups: the CTA owns the SM's whole TMEM
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
     __shared__ uint32_t tmem_slot;
@@ -266,7 +267,7 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
     constexpr int WFL = 2 * NP * KP + 2 * NP;
     copy_f4(sB, p.wpack, WFL, G * 128);
     publish_smem();
-    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
@@ -315,7 +316,7 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
             }
         });
     }
-    cta_teardown(&tmem_slot);
+    cta_teardown<TOT>(&tmem_slot);
 }
 
 // ===================================================================================================
@@ -1028,7 +1029,7 @@ int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, 
     };
     if (kind == 0) return run(tc_pw_kernel<96, 0, 0, 96, 2, true>, 96, 96, 2, 96);
     if (kind == 1) return run(tc_pw_kernel<192, 0, 0, 80, 2, true>, 192, 80, 2, 72);
-    if (kind == 2) return run(tc_pw_kernel<192, 96, 1, 80, 2, true>, 288, 80, 2, 72);
+    if (kind == 2) return run(tc_pw_kernel<192, 96, 1, 80, 4, true>, 288, 80, 4, 72);   // 184 KB of weights: one CTA per SM, so 4 groups
     set_error("tc_launch_pw: unknown kind %d", kind);
     return YFV2_EUNSUPPORTED;
 }

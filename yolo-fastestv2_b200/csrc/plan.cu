@@ -528,7 +528,7 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
         const int b = st.a;
         switch (st.kind) {
         case 0: {
-            if (getenv("YFV2_STEM_FFMA")) {
+            if (!getenv("YFV2_STEM_TC")) {   // default: register-tiled FFMA direct convolution (k_stem.cu explains why)
                 StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
                 TRY(launch_stem(a, s));
             } else {
