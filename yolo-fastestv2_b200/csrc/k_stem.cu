@@ -101,7 +101,7 @@ stem_kernel(const __grid_constant__ StemFArgs p) {
     };
 
     const int r = tid / S, s = tid - r * S;                  // conv row of the band / strip of 4 conv columns
-    const int lane = tid & 31, warp = tid >> 5;
+    const int p_oyl = tid / TWo, p_pc = tid - p_oyl * TWo;   // pooled pixel this thread writes in step 3
     uint32_t xpar = 0;
     if (blockIdx.x < items) stage(blockIdx.x);
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -188,13 +188,18 @@ stem_kernel(const __grid_constant__ StemFArgs p) {
                 *reinterpret_cast<float2*>(Hs + (ch * CR + r) * HSW + 2 * s) = make_float2(h0[ch], h1[ch]);
         }
         __syncthreads();                                      // B3
-        // ---- 3. vertical 3-max + ReLU -> output planes: warp <-> (channel, pooled row), lane <-> pooled column ------------
-        for (int pr = warp; pr < 24 * rows; pr += ST_THREADS / 32) {
-            const int ch = pr / rows, oyl = pr - ch * rows;
-            const float* hb = Hs + (ch * CR + 2 * oyl) * HSW;
-            float* op = plane_ptr(p.out, n, ch) + p.out.org + (oy0 + oyl) * p.out.Ws + ox0;
-            for (int pc = lane; pc < cols; pc += 32)
-                op[pc] = fmaxf(max3(hb[pc], hb[HSW + pc], hb[2 * HSW + pc]), 0.f);
+        // ---- 3. vertical 3-max + ReLU -> output planes: thread <-> pooled pixel of the tile, loop over the channels --------
+        if (p_oyl < rows && p_pc < cols) {
+            const float* hb = Hs + (2 * p_oyl) * HSW + p_pc;
+            float* op = plane_ptr(p.out, n, 0) + p.out.org + (oy0 + p_oyl) * p.out.Ws + ox0 + p_pc;
+            const int hstep = CR * HSW;
+            const size_t ostep = (size_t)p.out.sC;
+#pragma unroll 4
+            for (int ch = 0; ch < 24; ++ch) {
+                *op = fmaxf(max3(hb[0], hb[HSW], hb[2 * HSW]), 0.f);
+                hb += hstep;
+                op += ostep;
+            }
         }
     }
 }
@@ -219,7 +224,7 @@ int launch_stem(const StemArgs& a, cudaStream_t s) {
     while (k.TRo > 1 && stem_smem_bytes(k.TRo, k.TWo, k.S) > 112 * 1024) --k.TRo;
     if (k.TRo < 1) k.TRo = 1;
     const size_t bytes = stem_smem_bytes(k.TRo, k.TWo, k.S);
-    if ((2 * k.TRo + 1) * k.S > ST_THREADS || bytes > kSmemCap - 1024) { set_error("stem: unsupported geometry %dx%d", a.H, a.W); return YFV2_EUNSUPPORTED; }
+    if ((2 * k.TRo + 1) * k.S > ST_THREADS || k.TRo * k.TWo > ST_THREADS || bytes > kSmemCap - 1024) { set_error("stem: unsupported geometry %dx%d", a.H, a.W); return YFV2_EUNSUPPORTED; }
     k.tilesY = (HO + k.TRo - 1) / k.TRo;
     const int items = a.N * k.tilesX * k.tilesY;
     const int grid = items < 2 * sm_count() ? items : 2 * sm_count();
