@@ -106,6 +106,30 @@ __device__ __forceinline__ void cp_async_wait_all() {
 int sm_count();
 constexpr size_t kSmemCap = 227 * 1024;
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------
+// Every stage of a forward is its own kernel with a fixed prologue (weights -> shared memory, TMEM allocation, barrier
+// init: 5-15 us when ~300 CTAs pull the same weight pack out of L2).  None of that depends on the previous stage, so the
+// stage kernels are launched with programmatic stream serialization: a kernel may become resident while its predecessor
+// drains, runs its prologue, and executes pdl_wait() (griddepcontrol.wait: predecessor complete and its memory visible)
+// before it touches any activation.  pdl_trigger() at the top of every kernel lets the successor be scheduled as soon as
+// SM resources free up.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// The first kernel of a forward call is launched normally (its prologue may read weights an earlier pack kernel wrote).
+bool pdl_take();                 // true if the next launch may overlap its predecessor; arms the flag
+void pdl_reset();                // next launch is a plain one
+template <class Arg, class Kern>
+cudaError_t launch_k(Kern kern, int grid, int block, size_t smem, cudaStream_t s, bool pdl, const Arg& arg) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 // ---- kernel launchers (defined in the k_*.cu files) ---------------------------------------------------
 struct StemArgs {
     const void* x;       // [N,3,H,W] fp32 or uint8

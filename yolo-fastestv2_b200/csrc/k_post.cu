@@ -523,6 +523,7 @@ __device__ __forceinline__ void thread_cell_candidates(const PostGeom& g, const 
 
 __global__ void __launch_bounds__(NT, 2)
 decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smraw[];
     const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
     float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
@@ -686,7 +687,16 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
     const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (size_t)(5 * A + C) * kSStride * sizeof(float);
     if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
     YFV2_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    decode_nms_kernel<<<N, NT, bytes, (cudaStream_t)stream>>>(g, p, (C <= kCT && !getenv("YFV2_NMS_WARP_PER_CELL")) ? 1 : 0);
+    {   // nothing is read before pdl_wait(), so overlapping the predecessor's tail is always safe
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)N); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = bytes; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = getenv("YFV2_NO_PDL") ? 0 : 1;
+        const int fast = (C <= kCT && !getenv("YFV2_NMS_WARP_PER_CELL")) ? 1 : 0;
+        YFV2_CUDA(cudaLaunchKernelEx(&cfg, decode_nms_kernel, g, p, fast));
+    }
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }

@@ -42,6 +42,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(
 template <bool U8>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_kernel(const __grid_constant__ StemFArgs p) {
+    pdl_trigger();                                     // the first stride-2 block may start its prologue now
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t xbar;
     const int TRo = p.TRo, TWo = p.TWo, S = p.S;
@@ -59,6 +60,7 @@ stem_kernel(const __grid_constant__ StemFArgs p) {
     }
     if (tid == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
     __syncthreads();
+    pdl_wait();
     const int H = p.H, W = p.W, HC = H / 2, WC = W / 2, HO = H / 4, WO = W / 4;
     const int items = p.N * p.tilesX * p.tilesY;
 
@@ -117,12 +119,14 @@ stem_kernel(const __grid_constant__ StemFArgs p) {
         // ---- 1. conv: acc[j][ch], j = position 4s+j of conv row r (tile-local) ----------------------------------------
         float h0[24], h1[24];
         if (active) {
-            float acc[4][24];
+            // accumulators as channel pairs: the main loop is FFMA2 (fma.rn.f32x2, two IEEE fp32 FMAs per lane and issue
+            // slot, bit-identical to fmaf), which halves the issue pressure of the 2592-FMA body
+            float2 acc2[4][12];
 #pragma unroll
-            for (int ch = 0; ch < 24; ++ch) {
-                const float sh = sW[27 * 24 + ch];
+            for (int m = 0; m < 12; ++m) {
+                const float2 sh = *reinterpret_cast<const float2*>(sW + 27 * 24 + 2 * m);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j][ch] = sh;
+                for (int j = 0; j < 4; ++j) acc2[j][m] = sh;
             }
             const float* xb = Xin + (2 * r) * Wst + 8 * s;   // staged col of (position j, tap kx) = 8s + 2j + kx + 1
 #pragma unroll
@@ -133,24 +137,30 @@ stem_kernel(const __grid_constant__ StemFArgs p) {
                     const float4* xr = reinterpret_cast<const float4*>(xb + (c * IR + ky) * Wst);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) { const float4 v = xr[t]; x[4 * t] = v.x; x[4 * t + 1] = v.y; x[4 * t + 2] = v.z; x[4 * t + 3] = v.w; }
+                    float2 xx[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) xx[t] = make_float2(x[t + 1], x[t + 1]);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const float4* wr = reinterpret_cast<const float4*>(sW + ((c * 3 + ky) * 3 + kx) * 24);
 #pragma unroll
                         for (int q = 0; q < 6; ++q) {
                             const float4 w = wr[q];
+                            const float2 w01 = make_float2(w.x, w.y), w23 = make_float2(w.z, w.w);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float xv = x[2 * j + kx + 1];
-                                acc[j][4 * q] = fmaf(xv, w.x, acc[j][4 * q]);
-                                acc[j][4 * q + 1] = fmaf(xv, w.y, acc[j][4 * q + 1]);
-                                acc[j][4 * q + 2] = fmaf(xv, w.z, acc[j][4 * q + 2]);
-                                acc[j][4 * q + 3] = fmaf(xv, w.w, acc[j][4 * q + 3]);
+                                acc2[j][2 * q] = __ffma2_rn(xx[2 * j + kx], w01, acc2[j][2 * q]);
+                                acc2[j][2 * q + 1] = __ffma2_rn(xx[2 * j + kx], w23, acc2[j][2 * q + 1]);
                             }
                         }
                     }
                 }
             }
+            float acc[4][24];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < 12; ++m) { acc[j][2 * m] = acc2[j][m].x; acc[j][2 * m + 1] = acc2[j][m].y; }
             // conv positions outside the conv output never win a pool window
             const int cy = 2 * oy0 - 1 + r, cx = 2 * ox0 - 1 + 4 * s;
             const bool rowok = cy >= 0 && cy < HC;
@@ -230,10 +240,10 @@ int launch_stem(const StemArgs& a, cudaStream_t s) {
     const int grid = items < 2 * sm_count() ? items : 2 * sm_count();
     if (a.is_u8) {
         YFV2_CUDA(cudaFuncSetAttribute(stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        stem_kernel<true><<<grid, ST_THREADS, bytes, s>>>(k);
+        YFV2_CUDA(launch_k(stem_kernel<true>, grid, ST_THREADS, bytes, s, pdl_take(), k));
     } else {
         YFV2_CUDA(cudaFuncSetAttribute(stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        stem_kernel<false><<<grid, ST_THREADS, bytes, s>>>(k);
+        YFV2_CUDA(launch_k(stem_kernel<false>, grid, ST_THREADS, bytes, s, pdl_take(), k));
     }
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;

@@ -255,6 +255,7 @@ struct PwArgs {
 template <int KA, int KB, int SHA, int NP, int G, bool RELU>
 __global__ void __launch_bounds__(G * 128, (G * (kACols + NP) > kTmemCols) ? 1 : 2)
 tc_pw_kernel(const __grid_constant__ PwArgs p) {
+    pdl_trigger();
     constexpr int KP = KA + KB;
     constexpr int PF = 48;                                   // channels prefetched per batch of global loads
     static_assert(KP % PF == 0 && NP % 16 == 0, "shape");
@@ -268,6 +269,7 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
     copy_f4(sB, p.wpack, WFL, G * 128);
     publish_smem();
     Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
@@ -360,6 +362,7 @@ struct RowSink {
 template <int K, int NP, int G, int KS, int S, bool RELU_DW, bool RELU_OUT, bool DENSE>
 __global__ void __launch_bounds__(G * 128, 1)
 tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
+    pdl_trigger();
     constexpr int KP = K;
     static_assert(KP % 8 == 0 && NP % 16 == 0 && K <= G * 128, "shape");
     constexpr int COLS = kACols + NP;
@@ -379,14 +382,18 @@ tc_dwpw_kernel(const __grid_constant__ DwPwArgs p) {
     const int RS = RS1 * p.imgs;                           // plane stride of the staged buffer
     const int coff = p.in[0].pad - PADK;                   // frame column of the window's left edge for ox = 0
     if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
+    int loaded_branch = (int)(blockIdx.x % p.nbranch);     // the first item's weights are part of the prologue
+    copy_f4(sB, p.wpw[loaded_branch], WFL, G * 128);
+    copy_f4(sDW, p.wdw[loaded_branch], K * DWR, G * 128);
+    publish_smem();
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
     const int ngroups = (p.N + p.imgs - 1) / p.imgs;       // image groups
     const int items = ngroups * p.bandsPerImg * p.nbranch;
     const int grp = threadIdx.x >> 7;
-    int loaded_branch = -1;
     uint32_t xparity = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int br = item % p.nbranch;
@@ -458,6 +465,7 @@ constexpr int kHeadBufs = 4;
 template <int K, int NP, int G, bool DENSE>
 __global__ void __launch_bounds__(G * 128 + 32, 1)
 tc_head_kernel(const __grid_constant__ HeadArgs p) {
+    pdl_trigger();
     constexpr int NCH = K / 8, NB = kHeadBufs, DWR = 28, COLS = 128, TOT = 512;
     static_assert(K % 8 == 0 && NP % 16 == 0 && kACols + NP <= COLS && G * COLS <= TOT, "shape");
     extern __shared__ __align__(128) float smem[];
@@ -476,10 +484,17 @@ tc_head_kernel(const __grid_constant__ HeadArgs p) {
         for (int i = 0; i < NB; ++i) { mbar_init(&fullb[i], 1); mbar_init(&freeb[i], G * 4); }
         fence_mbar_init();
     }
-    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ngroups = (p.N + p.imgs - 1) / p.imgs;
     const int items = 2 * ngroups;                          // branch-major: item t -> (branch t / ngroups, group t % ngroups)
+    const int first_branch = (int)blockIdx.x / ngroups;     // < 2: the grid never exceeds `items`
+    if (threadIdx.x < G * 128) {                            // the first item's weights are part of the prologue
+        copy_f4(sB, p.wpw[first_branch], WFL, G * 128);
+        copy_f4(sDW, p.wdw[first_branch], K * DWR, G * 128);
+        publish_smem();
+    }
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t it = 0;                                        // chunks produced / consumed so far (same sequence on both sides)
     if (warp == G * 4) {
         // ---------------- producer warp ------------------------------------------------------------------------
@@ -506,7 +521,7 @@ tc_head_kernel(const __grid_constant__ HeadArgs p) {
         const float* shift = scale + NP;
         const int grp = threadIdx.x >> 7;
         const int HW = H * W;
-        int loaded_branch = -1;
+        int loaded_branch = first_branch;
         for (int t = blockIdx.x; t < items; t += gridDim.x) {
             const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
             const int nimg = min(p.imgs, p.N - n0);
@@ -564,6 +579,7 @@ struct S1Args {
 template <int K, int NP, int G>
 __global__ void __launch_bounds__(G * 128, 2)
 tc_s1_kernel(const __grid_constant__ S1Args p) {
+    pdl_trigger();
     constexpr int KP = K;
     constexpr int COLS = kACols + NP;
     extern __shared__ __align__(128) float smem[];
@@ -581,6 +597,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
     copy_f4(sDW, p.wdw, K * 12, G * 128);
     publish_smem();
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
     const uint32_t b2_hi = smem_u32(sB2), b2_lo = smem_u32(sB2 + NP * KP);
     const float* sc1 = sB1 + 2 * NP * KP; const float* sh1 = sc1 + NP;
@@ -664,6 +681,7 @@ struct S2Args {
 template <int K, int NP, int G>
 __global__ void __launch_bounds__(G * 128, 2)
 tc_s2_kernel(const __grid_constant__ S2Args p) {
+    pdl_trigger();
     constexpr int KP = K;
     constexpr int COLS = kACols + NP;
     static_assert(K <= G * 128, "one bulk copy per thread");
@@ -690,6 +708,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
     publish_smem();
     if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t bp_hi = smem_u32(sBp), bp_lo = smem_u32(sBp + NP * KP);
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
     const uint32_t b2_hi = smem_u32(sB2), b2_lo = smem_u32(sB2 + NP * KP);
@@ -792,6 +811,7 @@ struct StemTcArgs {
 template <bool U8>
 __global__ void __launch_bounds__(512, 2)
 tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
+    pdl_trigger();
     constexpr int G = 4, KP = 32, NP = 32, COLS = kACols + NP;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
@@ -809,6 +829,7 @@ tc_stem_kernel(const __grid_constant__ StemTcArgs p) {
     publish_smem();
     if (threadIdx.x == 0) { mbar_init(&xbar[0], 1); mbar_init(&xbar[1], 1); fence_mbar_init(); }
     Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
     const float* scale = sB + 2 * NP * KP;
     const float* shift = scale + NP;
@@ -959,10 +980,10 @@ int tc_launch_stem(const void* x, int is_u8, const Planes& out, const float* wpa
     const int items = N * a.tilesX * a.tilesY;
     if (is_u8) {
         TRYL(set_smem_attr(tc_stem_kernel<true>, bytes));
-        tc_stem_kernel<true><<<min(items, 2 * sm_count()), 512, bytes, s>>>(a);
+        YFV2_CUDA(launch_k(tc_stem_kernel<true>, min(items, 2 * sm_count()), 512, bytes, s, pdl_take(), a));
     } else {
         TRYL(set_smem_attr(tc_stem_kernel<false>, bytes));
-        tc_stem_kernel<false><<<min(items, 2 * sm_count()), 512, bytes, s>>>(a);
+        YFV2_CUDA(launch_k(tc_stem_kernel<false>, min(items, 2 * sm_count()), 512, bytes, s, pdl_take(), a));
     }
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
@@ -980,7 +1001,7 @@ int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout
         a.TR = TR; a.bandsPerImg = (H + TR - 1) / TR;
         TRYL(set_smem_attr(kern, bytes(TR)));
         const int items = N * a.bandsPerImg;
-        kern<<<min(items, 2 * sm_count()), G * 128, bytes(TR), s>>>(a);
+        YFV2_CUDA(launch_k(kern, min(items, 2 * sm_count()), G * 128, bytes(TR), s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
@@ -1002,7 +1023,7 @@ int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin,
         a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR;
         TRYL(set_smem_attr(kern, bytes(TR)));
         const int items = N * a.bandsPerImg;
-        kern<<<min(items, 2 * sm_count()), G * 128, bytes(TR), s>>>(a);
+        YFV2_CUDA(launch_k(kern, min(items, 2 * sm_count()), G * 128, bytes(TR), s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
@@ -1023,7 +1044,7 @@ int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, 
         const size_t bytes = (size_t)(2 * NP * KP + 2 * NP) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
         const int per_sm = bytes <= 110 * 1024 ? 2 : 1;
-        kern<<<min((ntiles + G - 1) / G, per_sm * sm_count()), G * 128, bytes, s>>>(a);
+        YFV2_CUDA(launch_k(kern, min((ntiles + G - 1) / G, per_sm * sm_count()), G * 128, bytes, s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
@@ -1062,7 +1083,7 @@ int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* t
         const size_t bytes = (wfl + (size_t)96 * (S * (a.TR - 1) + 3) * in[0].Ws * a.imgs + 4) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
         const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * nbranch;
-        kern<<<min(items, sm_count()), G * 128, bytes, s>>>(a);
+        YFV2_CUDA(launch_k(kern, min(items, sm_count()), G * 128, bytes, s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
@@ -1101,7 +1122,7 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
             const int ngroups = (N + a.imgs - 1) / a.imgs;
             auto run = [&](auto kern) -> int {
                 TRYL(set_smem_attr(kern, bytes));
-                kern<<<min(2 * ngroups, sm_count()), G * 128 + 32, bytes, s>>>(a);
+                YFV2_CUDA(launch_k(kern, min(2 * ngroups, sm_count()), G * 128 + 32, bytes, s, pdl_take(), a));
                 YFV2_LAUNCH_CHECK();
                 return YFV2_OK;
             };
@@ -1128,7 +1149,7 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         const size_t bytes = (wfl + (size_t)72 * (a.TR + 4) * sIn.Ws * a.imgs + 4) * sizeof(float);
         TRYL(set_smem_attr(kern, bytes));
         const int items = ((N + a.imgs - 1) / a.imgs) * a.bandsPerImg * 2;
-        kern<<<min(items, sm_count()), G * 128, bytes, s>>>(a);
+        YFV2_CUDA(launch_k(kern, min(items, sm_count()), G * 128, bytes, s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };

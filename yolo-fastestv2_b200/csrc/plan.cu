@@ -26,6 +26,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local bool g_pdl_next = false;
+static const bool g_pdl_off = getenv("YFV2_NO_PDL") != nullptr;
+bool pdl_take() { const bool r = g_pdl_next && !g_pdl_off; g_pdl_next = true; return r; }
+void pdl_reset() { g_pdl_next = false; }
+
 int sm_count() {
     static thread_local int n = 0;
     if (!n) {
@@ -511,6 +516,7 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
     if (first < 0 || last > p->n_stages || first > last) { set_error("forward: bad stage range [%d,%d)", first, last); return YFV2_EINVAL; }
     float* ws = (float*)workspace;
     const float* pk = (const float*)packed;
+    pdl_reset();                                            // the first kernel of this call is serialized normally
     if (p->ws_zeroed != workspace) {
         // the zero frames around every plane are never written afterwards (kernels store interior pixels only)
         YFV2_CUDA(cudaMemsetAsync(workspace, 0, p->ws_floats * sizeof(float), s));
