@@ -119,6 +119,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // The first kernel of a forward call is launched normally (its prologue may read weights an earlier pack kernel wrote).
 bool pdl_take();                 // true if the next launch may overlap its predecessor; arms the flag
 void pdl_reset();                // next launch is a plain one
+bool pdl_allowed();              // PDL enabled for the current API call
 template <class Arg, class Kern>
 cudaError_t launch_k(Kern kern, int grid, int block, size_t smem, cudaStream_t s, bool pdl, const Arg& arg) {
     cudaLaunchConfig_t cfg{};

@@ -693,7 +693,7 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = getenv("YFV2_NO_PDL") ? 0 : 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_allowed() ? 1 : 0;
         const int fast = (C <= kCT && !getenv("YFV2_NMS_WARP_PER_CELL")) ? 1 : 0;
         YFV2_CUDA(cudaLaunchKernelEx(&cfg, decode_nms_kernel, g, p, fast));
     }

@@ -565,6 +565,220 @@ tc_head_kernel(const __grid_constant__ HeadArgs p) {
 }
 
 // ===================================================================================================
+// tc_head2_kernel: tc_head_kernel with TWO pixels per thread.  The 5x5 stencil is bound by shared-memory wavefronts
+// (ncu: 48 % of the stalls are MIO throttle, 25 LDS per pixel-channel), so a thread takes a horizontally adjacent pixel
+// pair (x even): the six window columns of a row arrive as three LDS.64 and feed both pixels, the weights are loaded
+// once for the pair -> 18.5 instead of 32 wavefronts per 32 pixel-channels and 1.5x fewer instructions.  A thread can
+// only write its own TMEM lane, so the two pixels of a pair are the same row of two different M=128 tiles: a
+// warpgroup owns two accumulators (columns [64, 64+NP) and [64+NP, 64+2NP)) and the A ring holds both tiles' chunks
+// ([hi8|lo8] of tile 0, [hi8|lo8] of tile 1, twice).  2 warpgroups x 256 columns fill the SM's TMEM.
+// ===================================================================================================
+template <bool RELU>
+__device__ __forceinline__ void dw5_pair8(const float* __restrict__ xk, int RS, int WS, const float* __restrict__ wk, bool valid0, bool valid1,
+                                          float (&a0)[8], float (&a1)[8]) {
+    if (!valid0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float w[28];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * t);
+            w[4 * t] = w4.x; w[4 * t + 1] = w4.y; w[4 * t + 2] = w4.z; w[4 * t + 3] = w4.w;
+        }
+        float p0[5], p1[5];
+        const float* row = xk;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+            const float2 v01 = *reinterpret_cast<const float2*>(row);
+            const float2 v23 = *reinterpret_cast<const float2*>(row + 2);
+            const float2 v45 = *reinterpret_cast<const float2*>(row + 4);
+            const float v[6] = {v01.x, v01.y, v23.x, v23.y, v45.x, v45.y};
+            p0[dy] = w[dy * 5] * v[0];
+            p1[dy] = w[dy * 5] * v[1];
+#pragma unroll
+            for (int dx = 1; dx < 5; ++dx) {
+                p0[dy] = fmaf(w[dy * 5 + dx], v[dx], p0[dy]);
+                p1[dy] = fmaf(w[dy * 5 + dx], v[dx + 1], p1[dy]);
+            }
+            row += WS;
+        }
+        float d0 = ((p0[0] + p0[1]) + (p0[2] + p0[3])) + p0[4];      // same association as dw8p
+        float d1 = ((p1[0] + p1[1]) + (p1[2] + p1[3])) + p1[4];
+        d0 = fmaf(d0, w[25], w[26]);
+        d1 = fmaf(d1, w[25], w[26]);
+        if (RELU) { d0 = fmaxf(d0, 0.f); d1 = fmaxf(d1, 0.f); }
+        a0[j] = d0;
+        a1[j] = valid1 ? d1 : 0.f;
+        xk += RS;
+        wk += 28;
+    }
+}
+
+constexpr int kA2Cols = 64;             // 2 buffers x 2 tiles x (8 hi + 8 lo)
+
+template <int KP, int NP>
+__device__ __forceinline__ void put_chunk2(Grp& g, const float (&a0)[8], const float (&a1)[8], int c, uint32_t b_hi, uint32_t b_lo) {
+    const uint32_t buf = g.chunk & 1u, use = g.chunk >> 1;
+    if (use > 0) mbar_wait(&g.pipe->empty[buf], (use - 1) & 1u);
+    fence_after_sync();
+    store_a8(g.tlane + buf * 32, 8, a0);
+    store_a8(g.tlane + buf * 32 + 16, 8, a1);
+    wait_st();
+    fence_before_sync();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t old = atom_add_acq_rel(&g.pipe->arrivals[buf], 1u);
+        if ((old & 3u) == 3u) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NP);
+            constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
+            const uint64_t bh = make_b_desc(b_hi + c * 256, LBO, SBO);
+            const uint64_t bl = make_b_desc(b_lo + c * 256, LBO, SBO);
+#pragma unroll
+            for (int tile = 0; tile < 2; ++tile) {
+                const uint32_t a_hi = g.tcol + buf * 32 + tile * 16, a_lo = a_hi + 8, d = g.tcol + kA2Cols + tile * NP;
+                mma_tf32_ts(d, a_lo, bh, idesc, c > 0 ? 1u : 0u);
+                mma_tf32_ts(d, a_hi, bl, idesc, 1u);
+                mma_tf32_ts(d, a_hi, bh, idesc, 1u);
+            }
+            mma_commit(&g.pipe->empty[buf]);
+            if (c == KP / 8 - 1) mma_commit(&g.pipe->dfull);
+        }
+    }
+    __syncwarp();
+    ++g.chunk;
+}
+template <int NP, class Epi>
+__device__ __forceinline__ void get_tiles2(Grp& g, const Epi& epi0, const Epi& epi1, int ncols) {
+    mbar_wait(&g.pipe->dfull, g.dparity);
+    g.dparity ^= 1u;
+    fence_after_sync();
+#pragma unroll 1
+    for (int n0 = 0; n0 < ncols; n0 += 16) {                // rolled: the dense epilogue is long and identical per block
+        float d[16];
+        tmem_ld16(g.tlane + kA2Cols + n0, d);
+        wait_ld();
+        epi0(n0, d);
+    }
+#pragma unroll 1
+    for (int n0 = 0; n0 < ncols; n0 += 16) {
+        float d[16];
+        tmem_ld16(g.tlane + kA2Cols + NP + n0, d);
+        wait_ld();
+        epi1(n0, d);
+    }
+}
+
+template <int K, int NP, bool DENSE>
+__global__ void __launch_bounds__(2 * 128 + 32, 1)
+tc_head2_kernel(const __grid_constant__ HeadArgs p) {
+    pdl_trigger();
+    constexpr int G = 2, NCH = K / 8, NB = kHeadBufs, DWR = 28, COLS = 256, TOT = 512;
+    static_assert(K % 8 == 0 && NP % 16 == 0 && kA2Cols + 2 * NP <= COLS, "shape");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) Pipe pipes[G + 1];
+    __shared__ __align__(8) uint64_t fullb[NB], freeb[NB];
+    __shared__ uint32_t tmem_slot;
+    constexpr int WFL = 2 * NP * K + 2 * NP;
+    float* sB = smem;
+    float* sDW = sB + WFL;
+    float* X = sDW + K * DWR;
+    const int H = p.in[0].H, W = p.in[0].W, WS = p.in[0].Ws;
+    const int PS = (H + 4) * WS;
+    const int CS = PS * p.imgs;
+    const int BUF = 8 * CS;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullb[i], 1); mbar_init(&freeb[i], G * 4); }
+        fence_mbar_init();
+    }
+    const int ngroups = (p.N + p.imgs - 1) / p.imgs;
+    const int items = 2 * ngroups;
+    const int first_branch = (int)blockIdx.x / ngroups;
+    if (threadIdx.x < G * 128) {
+        copy_f4(sB, p.wpw[first_branch], WFL, G * 128);
+        copy_f4(sDW, p.wdw[first_branch], K * DWR, G * 128);
+        publish_smem();
+    }
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t it = 0;
+    if (warp == G * 4) {
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const uint32_t buf = it % NB, use = it / NB;
+                if (use > 0) mbar_wait(&freeb[buf], (use - 1) & 1u);
+                publish_smem();
+                if (lane == 0) mbar_expect_tx(&fullb[buf], (uint32_t)(8 * nimg * PS * sizeof(float)));
+                __syncwarp();
+                for (int j = lane; j < 8 * nimg; j += 32) {
+                    const int ch = j & 7, i = j >> 3;
+                    bulk_g2s(X + (size_t)buf * BUF + ch * CS + i * PS, plane_ptr(p.in[br], n0 + i, c * 8 + ch),
+                             (uint32_t)(PS * sizeof(float)), &fullb[buf]);
+                }
+            }
+        }
+    } else {
+        const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * K);
+        const float* scale = sB + 2 * NP * K;
+        const float* shift = scale + NP;
+        const int grp = threadIdx.x >> 7;
+        const int HW = H * W;
+        const int Wp = (W + 1) >> 1, PPI = H * Wp;          // pixel pairs per row / per image
+        int loaded_branch = first_branch;
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            if (br != loaded_branch) {
+                group_bar(1, G * 128);
+                copy_f4(sB, p.wpw[br], WFL, G * 128);
+                copy_f4(sDW, p.wdw[br], K * DWR, G * 128);
+                publish_smem();
+                group_bar(1, G * 128);
+                loaded_branch = br;
+            }
+            const int q = grp * 128 + g.gtid;               // pair index inside the item
+            const bool valid0 = q < PPI * nimg;
+            const int im = valid0 ? q / PPI : 0;
+            const int qi = valid0 ? q - im * PPI : 0;
+            const int oy = qi / Wp, ox = 2 * (qi - oy * Wp);
+            const bool valid1 = valid0 && ox + 1 < W;
+            const int woff = im * PS + oy * WS + ox;        // even: the three LDS.64 of a window row are aligned
+            RowSink<false, DENSE, true> sink0, sink1;
+            sink0.scale = scale; sink0.shift = shift; sink0.valid = valid0;
+            if (!DENSE) {
+                sink0.obase = p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox;
+                sink0.tout = nullptr; sink0.sCo = (unsigned)p.out[br].sC; sink0.nout = p.nout;
+            } else {
+                sink0.dA = p.dstA[br]; sink0.dB = p.dstB[br]; sink0.split = p.split[br]; sink0.M = p.M[br];
+                sink0.n = n0 + im; sink0.HW = HW; sink0.opix = oy * W + ox;
+            }
+            sink1 = sink0;
+            sink1.valid = valid1;
+            if (!DENSE) sink1.obase = sink0.obase + 1; else sink1.opix = sink0.opix + 1;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const uint32_t buf = it % NB;
+                mbar_wait(&fullb[buf], (it / NB) & 1u);
+                float a0[8], a1[8];
+                dw5_pair8<true>(X + (size_t)buf * BUF + woff, CS, WS, sDW + c * 8 * DWR, valid0, valid1, a0, a1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&freeb[buf]);
+                put_chunk2<K, NP>(g, a0, a1, c, b_hi, b_lo);
+            }
+            get_tiles2<NP>(g, sink0, sink1, DENSE ? p.M[br] : p.nout);
+        }
+    }
+    cta_teardown<TOT>(&tmem_slot);
+}
+
+// ===================================================================================================
 // tc_s1_kernel: fused stride-1 ShuffleV2 block (reference shufflenetv2.py:19-32,48-51).
 // ===================================================================================================
 struct S1Args {
@@ -1101,6 +1315,38 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
     const int np = half == 0 ? 80 : 96;
     static const bool force_band = getenv("YFV2_HEADS_BAND") != nullptr;
     // ---- fast path: channel-streamed whole-image items ----------------------------------------------------------
+    static const bool force_g4 = getenv("YFV2_HEADS_G4") != nullptr;
+    // pairs pay off when every pair is full (even W); odd maps (11x11) keep one pixel per thread
+    if (W % 2 == 0 && H * (W / 2) <= 256 && !force_band && !force_g4) {
+        // pixel pairs: 2 warpgroups x 2 tiles
+        HeadArgs a{};
+        a.N = N; a.nout = 72;
+        for (int b = 0; b < 2; ++b) { a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
+        if (half == 0) { a.in[0] = sIn; a.in[1] = sIn; a.out[0] = tcls; a.out[1] = treg; }
+        else {
+            a.in[0] = tcls; a.in[1] = treg;
+            a.dstA[0] = obj; a.dstB[0] = cls; a.split[0] = A; a.M[0] = A + C;
+            a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
+        }
+        const size_t PS = (size_t)(H + 4) * sIn.Ws;
+        const size_t wfl = (size_t)(2 * np * 72 + 2 * np) + 72 * 28;
+        const int PPI = H * ((W + 1) / 2);
+        a.imgs = 1;
+        while ((a.imgs + 1) * PPI <= 256 && a.imgs + 1 <= N &&
+               (wfl + kHeadBufs * 8 * PS * (a.imgs + 1) + 4) * sizeof(float) <= kSmemCap - 1024) ++a.imgs;
+        const size_t bytes = (wfl + kHeadBufs * 8 * PS * a.imgs + 4) * sizeof(float);
+        if (bytes <= kSmemCap - 1024) {
+            const int ngroups = (N + a.imgs - 1) / a.imgs;
+            auto run = [&](auto kern) -> int {
+                TRYL(set_smem_attr(kern, bytes));
+                YFV2_CUDA(launch_k(kern, min(2 * ngroups, sm_count()), 2 * 128 + 32, bytes, s, pdl_take(), a));
+                YFV2_LAUNCH_CHECK();
+                return YFV2_OK;
+            };
+            if (half == 0) return run(tc_head2_kernel<72, 80, false>);
+            return run(tc_head2_kernel<72, 96, true>);
+        }
+    }
     if (H * W <= 512 && !force_band) {
         constexpr int G = 4;
         HeadArgs a{};

@@ -27,9 +27,12 @@ void set_error(const char* fmt, ...) {
 }
 
 static thread_local bool g_pdl_next = false;
+static thread_local bool g_pdl_call = true;      // false inside yfv2_detect_u8_host: with copies and a second stream in flight the
+                                                 // early-resident dependents cost more than the hidden prologues save (measured)
 static const bool g_pdl_off = getenv("YFV2_NO_PDL") != nullptr;
-bool pdl_take() { const bool r = g_pdl_next && !g_pdl_off; g_pdl_next = true; return r; }
+bool pdl_take() { const bool r = g_pdl_next && g_pdl_call && !g_pdl_off; g_pdl_next = true; return r; }
 void pdl_reset() { g_pdl_next = false; }
+bool pdl_allowed() { return g_pdl_call && !g_pdl_off; }
 
 int sm_count() {
     static thread_local int n = 0;
@@ -663,6 +666,7 @@ extern "C" int yfv2_detect_u8_host(yfv2_plan* p, const uint8_t* x_host, const vo
     float* out_dev = (float*)(ws + L.off_out);
     int* counts_dev = (int*)(ws + L.off_counts);
     YFV2_CUDA(cudaMemcpyAsync(x_dev, x_host, (size_t)p->N * 3 * p->H * p->W, cudaMemcpyHostToDevice, s));
+    struct PdlOff { PdlOff() { g_pdl_call = false; } ~PdlOff() { g_pdl_call = true; } } pdl_off_guard;
     TRY(forward_impl(p, x_dev, 1, packed, preds, ws, 0, -1, s));
     TRY(yfv2_decode_nms(preds, p->N, p->H, p->W, p->A, p->C, anchors_host, conf_thres, iou_thres, nullptr, 0, max_det,
                         4096.0f, out_dev, counts_dev, nullptr, nullptr, stream));
