@@ -285,6 +285,9 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& 
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
+    // disjoint boxes (nearly every pair: other classes sit max_wh apart): IoU is 0, -0 or NaN, never above a threshold whose
+    // midpoint is positive -- same answer as the code below without its fp64 work
+    if (inter == 0.f && p.iou_mid > 0.0) return false;
     const float u = __fsub_rn(__fadd_rn(aa, ab), inter);
     if (u > 0.f && u < 3.0e38f && inter < 3.0e38f) {
         const double lhs = (double)inter, rhs = __dmul_rn(p.iou_mid, (double)u);
@@ -309,6 +312,60 @@ __device__ void bitonic_sort_desc(unsigned long long* keys, int n2) {
     }
 }
 
+// Same network with E = n2 / NT keys per thread held in registers (thread t owns elements [E t, E t + E)): strides below E
+// are compare-exchanges inside the thread, strides below 32 E are 64-bit warp shuffles, and only the log2(NT/32) largest
+// strides of the last merges (6 of the 66 steps for 2048 keys) go through shared memory and barriers.  The keys are
+// unique (or equal padding zeros), so every correct sorting network yields the same order as bitonic_sort_desc.
+template <int E>
+__device__ void bitonic_sort_desc_reg(unsigned long long* keys) {
+    constexpr int n2 = NT * E;
+    const int t = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = keys[E * t + m];
+#pragma unroll
+    for (int k = 2; k <= n2; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= E) {
+                unsigned long long o[E];
+                if (j >= 32 * E) {                       // partner thread t ^ (j / E) sits in another warp
+                    __syncthreads();                     // every earlier read of `keys` is done
+#pragma unroll
+                    for (int m = 0; m < E; ++m) keys[m * NT + t] = v[m];          // transposed: conflict-free both ways
+                    __syncthreads();
+#pragma unroll
+                    for (int m = 0; m < E; ++m) o[m] = keys[m * NT + (t ^ (j / E))];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) o[m] = __shfl_xor_sync(0xffffffffu, v[m], j / E);
+                }
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int i = E * t + m;
+                    const bool keep_max = ((i & k) == 0) == ((i & j) == 0);      // descending block: the lower index keeps the larger key
+                    const unsigned long long a = v[m], b = o[m];
+                    v[m] = keep_max ? (a > b ? a : b) : (a < b ? a : b);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    if ((m & j) == 0) {
+                        const int i = E * t + m;
+                        const unsigned long long a = v[m], b = v[m | j];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (a < b) : (a > b)) { v[m] = b; v[m | j] = a; }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < E; ++m) keys[E * t + m] = v[m];
+    __syncthreads();
+}
+
 // Sort the pushed candidates and run the blocked greedy suppression.  All threads of the CTA call this.
 __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
     __syncthreads();
@@ -317,7 +374,11 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
     while (n2 < cnt) n2 <<= 1;
     for (int i = cnt + threadIdx.x; i < n2; i += NT) s.keys[i] = 0ull;
     __syncthreads();
-    bitonic_sort_desc(s.keys, n2);
+    if (n2 == NT) bitonic_sort_desc_reg<1>(s.keys);
+    else if (n2 == 2 * NT) bitonic_sort_desc_reg<2>(s.keys);
+    else if (n2 == 4 * NT) bitonic_sort_desc_reg<4>(s.keys);
+    else if (n2 == 8 * NT) bitonic_sort_desc_reg<8>(s.keys);
+    else bitonic_sort_desc(s.keys, n2);
 
     float* out = p.out + (long long)n * p.max_det * 6;
     int* kidx = p.kept_idx ? p.kept_idx + (long long)n * p.max_det : nullptr;

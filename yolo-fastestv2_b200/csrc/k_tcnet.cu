@@ -791,11 +791,12 @@ struct S1Args {
 };
 
 template <int K, int NP, int G>
-__global__ void __launch_bounds__(G * 128, 2)
+__global__ void __launch_bounds__(G * 128, (G * (kACols + NP) > kTmemCols) ? 1 : 2)
 tc_s1_kernel(const __grid_constant__ S1Args p) {
     pdl_trigger();
     constexpr int KP = K;
     constexpr int COLS = kACols + NP;
+    constexpr int TOT = (G * COLS > kTmemCols) ? 512 : kTmemCols;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
     __shared__ uint32_t tmem_slot;
@@ -810,7 +811,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
     copy_f4(sB2, p.w2, WFL, G * 128);
     copy_f4(sDW, p.wdw, K * 12, G * 128);
     publish_smem();
-    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
     pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
     const uint32_t b2_hi = smem_u32(sB2), b2_lo = smem_u32(sB2 + NP * KP);
@@ -878,7 +879,7 @@ tc_s1_kernel(const __grid_constant__ S1Args p) {
                 });
         }
     }
-    cta_teardown(&tmem_slot);
+    cta_teardown<TOT>(&tmem_slot);
 }
 
 // ===================================================================================================
@@ -893,11 +894,12 @@ struct S2Args {
 };
 
 template <int K, int NP, int G>
-__global__ void __launch_bounds__(G * 128, 2)
+__global__ void __launch_bounds__(G * 128, (G * (kACols + NP) > kTmemCols) ? 1 : 2)
 tc_s2_kernel(const __grid_constant__ S2Args p) {
     pdl_trigger();
     constexpr int KP = K;
     constexpr int COLS = kACols + NP;
+    constexpr int TOT = (G * COLS > kTmemCols) ? 512 : kTmemCols;
     static_assert(K <= G * 128, "one bulk copy per thread");
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
@@ -921,7 +923,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
     copy_f4(sDWm, p.wdwm, K * 12, G * 128);
     publish_smem();
     if (threadIdx.x == 0) { mbar_init(&xbar, 1); fence_mbar_init(); }
-    Grp g = cta_setup<G, COLS>(pipes, &tmem_slot);
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
     pdl_wait();                                            // predecessor's activations are complete and visible from here on
     const uint32_t bp_hi = smem_u32(sBp), bp_lo = smem_u32(sBp + NP * KP);
     const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
@@ -1004,7 +1006,7 @@ tc_s2_kernel(const __grid_constant__ S2Args p) {
                 });
         }
     }
-    cta_teardown(&tmem_slot);
+    cta_teardown<TOT>(&tmem_slot);
 }
 
 // ===================================================================================================
@@ -1207,20 +1209,22 @@ int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout
                  int N, cudaStream_t s) {
     S1Args a{P, tin, tout, w1, wdw, w2, N, 0, 0};
     const int H = P.H, W = P.W;
-    auto run = [&](auto kern, int KK, int NP, int G) -> int {
+    auto run = [&](auto kern, int KK, int NP, int G, bool one_per_sm) -> int {
         const size_t wfl = (size_t)2 * (2 * NP * KK + 2 * NP) + KK * 12;
         auto bytes = [&](int tr) { return (wfl + (size_t)KK * (tr + 2) * (W + 2) + 4) * sizeof(float); };
+        const size_t cap = one_per_sm ? 215 * 1024 : 110 * 1024;       // one or two CTAs per SM
         int TR = H;
-        while (TR > 1 && bytes(TR) > 110 * 1024) TR = (TR + 1) / 2;     // two CTAs per SM
+        while (TR > 1 && bytes(TR) > cap) TR = (TR + 1) / 2;
         a.TR = TR; a.bandsPerImg = (H + TR - 1) / TR;
         TRYL(set_smem_attr(kern, bytes(TR)));
         const int items = N * a.bandsPerImg;
-        YFV2_CUDA(launch_k(kern, min(items, 2 * sm_count()), G * 128, bytes(TR), s, pdl_take(), a));
+        YFV2_CUDA(launch_k(kern, min(items, (one_per_sm ? 1 : 2) * sm_count()), G * 128, bytes(TR), s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (K == 24) return run(tc_s1_kernel<24, 32, 4>, 24, 32, 4);
-    if (K == 48) return run(tc_s1_kernel<48, 48, 3>, 48, 48, 3);
+    // (measured: whole-image items with 4 groups on one CTA per SM are 5 % slower for K=48 than two half-image CTAs)
+    if (K == 24) return run(tc_s1_kernel<24, 32, 4>, 24, 32, 4, false);
+    if (K == 48) return run(tc_s1_kernel<48, 48, 3>, 48, 48, 3, false);
     set_error("tc_launch_s1: unsupported K=%d", K);
     return YFV2_EUNSUPPORTED;
 }
@@ -1229,20 +1233,23 @@ int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin,
                  const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s) {
     S2Args a{in, out, tin, tout, wdwp, wp, w1, wdwm, w2, N, 0, 0};
     const int Hout = out.H;
-    auto run = [&](auto kern, int KK, int NP, int G) -> int {
+    auto run = [&](auto kern, int KK, int NP, int G, bool one_per_sm) -> int {
         const size_t wfl = (size_t)3 * (2 * NP * KK + 2 * NP) + 2 * KK * 12;
         auto bytes = [&](int tr) { return (wfl + (size_t)KK * (2 * tr + 1) * in.Ws + 4) * sizeof(float); };
+        const size_t cap = one_per_sm ? 218 * 1024 : 110 * 1024;
         int TR = Hout;
-        while (TR > 1 && bytes(TR) > 110 * 1024) --TR;
+        while (TR > 1 && bytes(TR) > cap) --TR;
         a.TR = TR; a.bandsPerImg = (Hout + TR - 1) / TR;
         TRYL(set_smem_attr(kern, bytes(TR)));
         const int items = N * a.bandsPerImg;
-        YFV2_CUDA(launch_k(kern, min(items, 2 * sm_count()), G * 128, bytes(TR), s, pdl_take(), a));
+        YFV2_CUDA(launch_k(kern, min(items, (one_per_sm ? 1 : 2) * sm_count()), G * 128, bytes(TR), s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
-    if (K == 24) return run(tc_s2_kernel<24, 32, 4>, 24, 32, 4);
-    if (K == 48) return run(tc_s2_kernel<48, 48, 3>, 48, 48, 3);
+    // K=48: three 18.8 KB weight packs leave two co-resident CTAs only 2-row bands (one third-full tile per phase);
+    // one CTA per SM with 8-row bands and 4 groups is 15 % faster (201 -> 171 us).  K=24: the opposite (197 vs 229 us).
+    if (K == 24) return run(tc_s2_kernel<24, 32, 4>, 24, 32, 4, false);
+    if (K == 48) return run(tc_s2_kernel<48, 48, 4>, 48, 48, 4, true);
     set_error("tc_launch_s2: unsupported K=%d", K);
     return YFV2_EUNSUPPORTED;
 }
