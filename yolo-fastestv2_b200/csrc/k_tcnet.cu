@@ -39,9 +39,10 @@ using namespace tc;
 constexpr int kTmemCols = 256;          // per CTA; every kernel here allocates the same amount (two CTAs fill an SM's 512)
 constexpr int kACols = 32;             // 2 buffers x (8 hi + 8 lo)
 
+constexpr int kMaxABufs = 4;
 struct Pipe {                          // per group, in shared memory
-    uint64_t empty[2], dfull;
-    uint32_t arrivals[2];
+    uint64_t empty[kMaxABufs], dfull;
+    uint32_t arrivals[kMaxABufs];
     uint32_t pad_[2];
 };
 
@@ -72,9 +73,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // Hand chunk c (8 channels of this thread's pixel) of a KP->NP contraction to the tensor core.
 //   b_hi / b_lo: shared addresses of the weight pack; `last`: this is the tile's final chunk.
-template <int KP, int NP>
+//   NB: A buffers in the ring (2 everywhere; the accumulator then starts at column 16*NB of the group's block)
+template <int KP, int NP, int NB = 2>
 __device__ __forceinline__ void put_chunk(Grp& g, const float (&a)[8], int c, uint32_t b_hi, uint32_t b_lo) {
-    const uint32_t buf = g.chunk & 1u, use = g.chunk >> 1;
+    static_assert(NB >= 2 && NB <= kMaxABufs, "A ring depth");
+    const uint32_t buf = g.chunk % NB, use = g.chunk / NB;
     if (use > 0) mbar_wait(&g.pipe->empty[buf], (use - 1) & 1u);     // the MMAs that read this buffer last time are done
     fence_after_sync();
     store_a8(g.tlane + buf * 16, 8, a);
@@ -87,7 +90,7 @@ __device__ __forceinline__ void put_chunk(Grp& g, const float (&a)[8], int c, ui
             fence_after_sync();
             constexpr uint32_t idesc = make_idesc_tf32(128, NP);
             constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
-            const uint32_t a_hi = g.tcol + buf * 16, a_lo = a_hi + 8, d = g.tcol + kACols;
+            const uint32_t a_hi = g.tcol + buf * 16, a_lo = a_hi + 8, d = g.tcol + 16 * NB;
             const uint64_t bh = make_b_desc(b_hi + c * 256, LBO, SBO);
             const uint64_t bl = make_b_desc(b_lo + c * 256, LBO, SBO);
             mma_tf32_ts(d, a_lo, bh, idesc, c > 0 ? 1u : 0u);        // small terms first
@@ -101,7 +104,7 @@ __device__ __forceinline__ void put_chunk(Grp& g, const float (&a)[8], int c, ui
     ++g.chunk;
 }
 // Collect the NP output columns of this thread's pixel.
-template <int NP, class Epi>
+template <int NP, int NB = 2, class Epi>
 __device__ __forceinline__ void get_tile(Grp& g, Epi&& epi, int ncols = NP) {
     mbar_wait(&g.pipe->dfull, g.dparity);
     g.dparity ^= 1u;
@@ -110,7 +113,7 @@ __device__ __forceinline__ void get_tile(Grp& g, Epi&& epi, int ncols = NP) {
     for (int n0 = 0; n0 < NP; n0 += 16) {
         if (n0 >= ncols) break;                 // trailing all-padding column blocks (warp-uniform)
         float d[16];
-        tmem_ld16(g.tlane + kACols + n0, d);
+        tmem_ld16(g.tlane + 16 * NB + n0, d);
         wait_ld();
         epi(n0, d);
     }
@@ -148,9 +151,8 @@ __device__ __forceinline__ Grp cta_setup(Pipe* pipes, uint32_t* tmem_slot) {
     if (warp == 0) tmem_alloc(tmem_slot, TOT);
     if (threadIdx.x == 32) {
         for (int i = 0; i < G; ++i) {
-            mbar_init(&pipes[i].empty[0], 1); mbar_init(&pipes[i].empty[1], 1);
+            for (int b = 0; b < kMaxABufs; ++b) { mbar_init(&pipes[i].empty[b], 1); pipes[i].arrivals[b] = 0; }
             mbar_init(&pipes[i].dfull, 1);
-            pipes[i].arrivals[0] = 0; pipes[i].arrivals[1] = 0;
         }
         fence_mbar_init();
     }
@@ -252,14 +254,14 @@ struct PwArgs {
     int nout;               // real output channels
 };
 
-template <int KA, int KB, int SHA, int NP, int G, bool RELU>
-__global__ void __launch_bounds__(G * 128, (G * (kACols + NP) > kTmemCols) ? 1 : 2)
+template <int KA, int KB, int SHA, int NP, int G, bool RELU, int NB = 2>
+__global__ void __launch_bounds__(G * 128, (G * (16 * NB + NP) > kTmemCols) ? 1 : 2)
 tc_pw_kernel(const __grid_constant__ PwArgs p) {
     pdl_trigger();
     constexpr int KP = KA + KB;
     constexpr int PF = 48;                                   // channels prefetched per batch of global loads
     static_assert(KP % PF == 0 && NP % 16 == 0, "shape");
-    constexpr int COLS = kACols + NP;
+    constexpr int COLS = 16 * NB + NP;                       // NB-deep A ring + accumulator
     constexpr int TOT = (G * COLS > kTmemCols) ? 512 : kTmemCols;   // 4 groups: the CTA owns the SM's whole TMEM
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) Pipe pipes[G];
@@ -301,10 +303,10 @@ tc_pw_kernel(const __grid_constant__ PwArgs p) {
                 float a[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a[j] = v[c * 8 + j];
-                put_chunk<KP, NP>(g, a, kb / 8 + c, b_hi, b_lo);
+                put_chunk<KP, NP, NB>(g, a, kb / 8 + c, b_hi, b_lo);
             }
         }
-        get_tile<NP>(g, [&](int n0, float (&d)[16]) {
+        get_tile<NP, NB>(g, [&](int n0, float (&d)[16]) {
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -1271,6 +1273,8 @@ int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, 
     };
     if (kind == 0) return run(tc_pw_kernel<96, 0, 0, 96, 2, true>, 96, 96, 2, 96);
     if (kind == 1) return run(tc_pw_kernel<192, 0, 0, 80, 2, true>, 192, 80, 2, 72);
+    static const bool nb3 = getenv("YFV2_FPN_NB3") != nullptr;    // experiment: 3-deep A ring (48 + 80 = 128 columns per group)
+    if (kind == 2 && nb3) return run(tc_pw_kernel<192, 96, 1, 80, 4, true, 3>, 288, 80, 4, 72);
     if (kind == 2) return run(tc_pw_kernel<192, 96, 1, 80, 4, true>, 288, 80, 4, 72);   // 184 KB of weights: one CTA per SM, so 4 groups
     set_error("tc_launch_pw: unknown kind %d", kind);
     return YFV2_EUNSUPPORTED;
