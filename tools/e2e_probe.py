@@ -1,5 +1,5 @@
 """H2D bandwidth and e2e variants (streams / buffers) for yfv2_detect_u8_host."""
-import sys; sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+import os, sys; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch, time
 import bench, yfv2, yfv2_engine as eng
 dev = torch.device("cuda", 0)

@@ -1,4 +1,4 @@
-import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import os, sys; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import contextlib, torch
 import bench, yfv2, yfv2_engine as eng
 dev = torch.device("cuda", 0)
