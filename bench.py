@@ -274,26 +274,46 @@ def run_ours(args, rank, world, local_rank):
         reps = max(3, min(args.steps, 10))
         plan.forward(x, preds)
         unit_bytes = dict(zip(UNIT_NAMES, bpi))
+        # one timing per kernel launch: consecutive stages with the same stage_groups value are one chained launch
+        groups = []
+        for st, gid in enumerate(plan.stage_groups):
+            if groups and groups[-1][0] == gid:
+                groups[-1][2] = st + 1
+            else:
+                groups.append([gid, st, st + 1])
         launches = []
-        for st, name in enumerate(plan.stage_names):
+        for _, first, last in groups:
             tot = 0.0
             for _ in range(reps):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
-                plan.forward_range(x, preds, st, st + 1)
+                plan.forward_range(x, preds, first, last)
                 b.record(stream)
                 b.synchronize()
                 tot += a.elapsed_time(b)
-            launches.append((name, 1e3 * tot / reps))
-        # a fused unit of SURVEY 8(d) may be more than one launch (K=96 blocks: pw1 + dw/pw2): sum them per unit
+            units = []
+            for n_ in plan.stage_names[first:last]:
+                if n_.split("/")[0] not in units:
+                    units.append(n_.split("/")[0])
+            launches.append((units, 1e3 * tot / reps))
+        # a fused unit of SURVEY 8(d) may be more than one launch (K=96 blocks: pw1 + dw/pw2: summed), and one launch may
+        # cover several units (chained stride-1 blocks: their algorithmic bytes are summed)
         stages = []
-        for unit in UNIT_NAMES:
-            parts = [(n_, us_) for n_, us_ in launches if n_.split("/")[0] == unit]
-            us = sum(us_ for _, us_ in parts)
-            gbs = unit_bytes[unit] * BATCH / (us * 1e-6) / 1e9
-            stages.append({"stage": unit, "us": round(us, 2), "launches": len(parts), "alg_MB": round(unit_bytes[unit] * BATCH / 1e6, 2),
-                           "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)})
+        for units, us in launches:
+            if stages and stages[-1]["_units"] == units:
+                stages[-1]["us"] += us
+                stages[-1]["launches"] += 1
+                continue
+            label = units[0] if len(units) == 1 else "%s-%s" % (units[0], units[-1].split(".")[-1])
+            stages.append({"stage": label, "us": us, "launches": 1, "_units": units,
+                           "alg_MB": round(sum(unit_bytes[u] for u in units) * BATCH / 1e6, 2)})
+        for s_ in stages:
+            gbs = s_["alg_MB"] * 1e6 / (s_["us"] * 1e-6) / 1e9
+            s_["units"] = len(s_.pop("_units"))
+            s_["us"] = round(s_["us"], 2)
+            s_["GBps"] = round(gbs, 1)
+            s_["frac"] = round(gbs / peak, 4)
         top = max(stages, key=lambda s: s["us"])
         bb = [s for s in stages if s["stage"].startswith(("stem", "stage"))]
         bb_bytes = sum(s["alg_MB"] for s in bb) * 1e6

@@ -164,13 +164,15 @@ YFV2_API int yfv2_op_upsample2_fwd(const float* x, float* y, int planes, int H, 
 YFV2_API int yfv2_op_upsample2_bwd(const float* dy, float* dx, int planes, int H, int W, void* stream);
 
 /* ---- stage-granular forward (profiling / tests) ---------------------------------------------------------
- * A forward is yfv2_plan_forward_launches() fused stages, one kernel launch each; yfv2_plan_stage_name(i) names
- * them ("stem", "stage2.0", ..., "stage4.1/pw1", "stage4.1/dwpw", "fpn.S3", "fpn.S2", "heads2.a", ...).
- * yfv2_forward_range runs stages [first,last) (last < 0: to the end).  bench.py times single stages with it; a
- * block's output is only intact until a later stage recycles its planes.  The stage list depends on the
- * engine: tcgen05 kernels by default, the FFMA kernels when the environment has YFV2_ENGINE=ffma at
- * plan-creation time. */
+ * A forward is a list of fused stages; yfv2_plan_stage_name(i) names them ("stem", "stage2.0", ...,
+ * "stage4.1/pw1", "stage4.1/dwpw", "fpn.S3", "fpn.S2", "heads2.a", ...).  yfv2_forward_range runs stages
+ * [first,last) (last < 0: to the end).  Consecutive stages with the same yfv2_plan_stage_group() value are ONE
+ * kernel launch when the range covers them (chained stride-1 ShuffleV2 blocks, csrc/k_blk.cu); a range that cuts
+ * a group runs the covered part as its own launch, so every block output can still be tapped.
+ * yfv2_plan_forward_launches() counts the launches of a whole forward.  A block's output is only intact until a
+ * later stage recycles its planes. */
 YFV2_API const char* yfv2_plan_stage_name(const yfv2_plan* plan, int i);
+YFV2_API int yfv2_plan_stage_group(const yfv2_plan* plan, int i);    /* index of the first stage of stage i's launch; -1: bad i */
 YFV2_API int yfv2_forward_range(yfv2_plan* plan, const void* x, int is_u8, const void* packed, float* const preds[6],
                                 void* workspace, int first, int last, void* stream);
 

@@ -17,6 +17,8 @@
 
 namespace yfv2 {
 
+bool blk_s1_chainable(int K, int H, int W);      // k_blk.cu
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -193,7 +195,7 @@ struct yfv2_plan {
     size_t tk_fold[4], pk_foldw[4];    // heads' second pointwise + BN + output conv folded into one matrix (tc pack / fp32 scratch)
     ChanTab t96;                       // scratch plane ids for the K=96 blocks' pw1 output
     int n_stages;
-    struct Stage { int kind, a, b; char name[24]; } stages[64];
+    struct Stage { int kind, a, b; char name[24]; int group; } stages[64];   // group: first stage of the launch this stage shares
 };
 
 namespace {
@@ -340,7 +342,16 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     }
     add(14, 1, 0, "fpn.S3", 0, 0); add(14, 2, 0, "fpn.S2", 0, 0);
     for (int lv = 0; lv < 2; ++lv) { add(15, lv, 0, "heads%d.a", lv + 2, 0); add(15, lv, 1, "heads%d.b", lv + 2, 0); }
-    p->launches = p->n_stages;
+    // launch groups: consecutive stride-1 blocks of a stage run as one chained launch when an image fits (k_blk.cu)
+    p->launches = 0;
+    for (int i = 0; i < p->n_stages; ++i) {
+        yfv2_plan::Stage& st = p->stages[i];
+        st.group = i;
+        if (i > 0 && st.kind == 10 && p->stages[i - 1].kind == 10 && p->blk_K[st.a] == p->blk_K[p->stages[i - 1].a] &&
+            i - p->stages[i - 1].group < 7 && blk_s1_chainable(p->blk_K[st.a], p->h[p->blk_res[st.a]], p->w[p->blk_res[st.a]]))
+            st.group = p->stages[i - 1].group;
+        if (st.group == i) ++p->launches;
+    }
     *out = p;
     return YFV2_OK;
 }
@@ -365,6 +376,11 @@ extern "C" int yfv2_plan_packed_bytes(const yfv2_plan* p, size_t* bytes) {
 extern "C" const char* yfv2_plan_stage_name(const yfv2_plan* p, int i) {
     if (!p || i < 0 || i >= p->n_stages) return nullptr;
     return p->stages[i].name;
+}
+
+extern "C" int yfv2_plan_stage_group(const yfv2_plan* p, int i) {
+    if (!p || i < 0 || i >= p->n_stages) return -1;
+    return p->stages[i].group;
 }
 
 extern "C" int yfv2_plan_forward_launches(const yfv2_plan* p, int* n) {
@@ -507,6 +523,10 @@ int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* t
                      const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
 int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
                     float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s);
+// k_blk.cu
+bool blk_s1_chainable(int K, int H, int W);
+int blk_launch_s1(int K, const Planes& P, int nblk, const ChanTab* tin, const ChanTab* tout, const float* const* w1,
+                  const float* const* wdw, const float* const* w2, int N, cudaStream_t s, int* done);
 }
 
 namespace {
@@ -559,11 +579,28 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             TRY(tc_launch_heads(half, sIn, t_cls, t_reg, wdw, wpw, preds[3 * lv], preds[3 * lv + 1],
                                 preds[3 * lv + 2], p->A, p->C, p->N, s));
         } break;
-        case 10: {   // tc fused stride-1 block
+        case 10: {   // fused stride-1 blocks; consecutive blocks of a stage inside [first, last) share one launch when
+                     // an image's intermediate fits in shared memory (k_blk.cu)
             const int K = p->blk_K[b];
-            const float* d = pk + p->pk_block[b];
-            TRY(tc_launch_s1(K, pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b], pk + p->tk_blk[b][0],
-                             d + pw_pack_floats(K, K), pk + p->tk_blk[b][1], p->N, s));
+            static const bool old_s1 = getenv("YFV2_S1_OLD") != nullptr;          // round-1 kernel, kept for A/B runs
+            if (old_s1) {
+                const float* d = pk + p->pk_block[b];
+                TRY(tc_launch_s1(K, pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b], pk + p->tk_blk[b][0],
+                                 d + pw_pack_floats(K, K), pk + p->tk_blk[b][1], p->N, s));
+                break;
+            }
+            int nb = 1;
+            while (si + nb < last && p->stages[si + nb].group == st.group) ++nb;
+            const float *w1[8], *w2[8], *wd[8];
+            if (nb > 7) nb = 7;
+            for (int j = 0; j < nb; ++j) {
+                const int bj = b + j;
+                w1[j] = pk + p->tk_blk[bj][0]; w2[j] = pk + p->tk_blk[bj][1];
+                wd[j] = pk + p->pk_block[bj] + pw_pack_floats(K, K);
+            }
+            int done = 1;
+            TRY(blk_launch_s1(K, pool_planes(p, ws, p->blk_res[b]), nb, &p->tin[b], &p->tout[b], w1, wd, w2, p->N, s, &done));
+            si += done - 1;
         } break;
         case 11: {   // tc fused stride-2 block
             const int K = p->blk_K[b];

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "yfv2_op_upsample2_fwd": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     "yfv2_op_upsample2_bwd": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     "yfv2_plan_stage_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
+    "yfv2_plan_stage_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yfv2_forward_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _c_void_pp,
                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "yfv2_debug_pw_tc": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
@@ -152,7 +153,13 @@ class Plan:
         n = ctypes.c_int()
         _check(L.yfv2_plan_forward_launches(self._h, ctypes.byref(n)), "forward_launches")
         self.forward_launches = n.value
-        self.stage_names = [L.yfv2_plan_stage_name(self._h, i).decode() for i in range(n.value)]
+        self.stage_names = []                 # fused stages; stages sharing a stage_groups value are one kernel launch
+        while True:
+            nm = L.yfv2_plan_stage_name(self._h, len(self.stage_names))
+            if nm is None:
+                break
+            self.stage_names.append(nm.decode())
+        self.stage_groups = [L.yfv2_plan_stage_group(self._h, i) for i in range(len(self.stage_names))]
         self.packed_version = None
 
     def __del__(self):
