@@ -18,6 +18,7 @@
 namespace yfv2 {
 
 bool blk_s1_chainable(int K, int H, int W);      // k_blk.cu
+bool tail_s1_supported(int K, int H, int W);     // k_tail.cu
 
 static thread_local char g_err[512] = "";
 
@@ -337,6 +338,7 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     add(0, 0, 0, "stem", 0, 0);
     for (int b = 0, st = 0, rep = 0; b < kNumBlocks; ++b) {
         if (p->blk_K[b] < 96) add(p->blk_stride[b] == 2 ? 11 : 10, b, 0, "stage%d.%d", st + 2, rep);
+        else if (p->blk_stride[b] == 1 && tail_s1_supported(96, p->h[3], p->w[3])) add(16, b, 0, "stage%d.%d", st + 2, rep);   // small-map chain
         else { add(12, b, 0, "stage%d.%d/pw1", st + 2, rep); add(13, b, 0, "stage%d.%d/dwpw", st + 2, rep); }
         if (++rep == kStageRepeats[st]) { rep = 0; ++st; }
     }
@@ -350,6 +352,7 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
         if (i > 0 && st.kind == 10 && p->stages[i - 1].kind == 10 && p->blk_K[st.a] == p->blk_K[p->stages[i - 1].a] &&
             i - p->stages[i - 1].group < 7 && blk_s1_chainable(p->blk_K[st.a], p->h[p->blk_res[st.a]], p->w[p->blk_res[st.a]]))
             st.group = p->stages[i - 1].group;
+        if (i > 0 && st.kind == 16 && p->stages[i - 1].kind == 16 && i - p->stages[i - 1].group < 4) st.group = p->stages[i - 1].group;
         if (st.group == i) ++p->launches;
     }
     *out = p;
@@ -527,6 +530,9 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
 bool blk_s1_chainable(int K, int H, int W);
 int blk_launch_s1(int K, const Planes& P, int nblk, const ChanTab* tin, const ChanTab* tout, const float* const* w1,
                   const float* const* wdw, const float* const* w2, int N, cudaStream_t s, int* done);
+// k_tail.cu
+int tail_launch_s1(const Planes& P, int nblk, const ChanTab* tin, const ChanTab* tout, const float* const* w1,
+                   const float* const* wdw, const float* const* w2, int N, cudaStream_t s, int* done);
 }
 
 namespace {
@@ -608,6 +614,20 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             const int dwn = dw3_pack_floats(K), pwn = pw_pack_floats(K, K);
             TRY(tc_launch_s2(K, pool_planes(p, ws, p->blk_res[b] - 1), pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b],
                              d, pk + p->tk_blk[b][2], pk + p->tk_blk[b][0], d + dwn + 2 * pwn, pk + p->tk_blk[b][1], p->N, s));
+        } break;
+        case 16: {   // K=96 stride-1 blocks on a map of at most 128 pixels: one chained launch (k_tail.cu)
+            int nb = 1;
+            while (si + nb < last && p->stages[si + nb].group == st.group) ++nb;
+            const float *w1[4], *w2[4], *wd[4];
+            if (nb > 4) nb = 4;
+            for (int j = 0; j < nb; ++j) {
+                const int bj = b + j;
+                w1[j] = pk + p->tk_blk[bj][0]; w2[j] = pk + p->tk_blk[bj][1];
+                wd[j] = pk + p->pk_block[bj] + pw_pack_floats(96, 96);
+            }
+            int done = 1;
+            TRY(tail_launch_s1(pool_planes(p, ws, p->blk_res[b]), nb, &p->tin[b], &p->tout[b], w1, wd, w2, p->N, s, &done));
+            si += done - 1;
         } break;
         case 12: case 13: {   // K=96 blocks: pw1 (global -> scratch planes), then dw3x3 -> pw2 (+ proj branch when stride 2)
             const int stride = p->blk_stride[b];

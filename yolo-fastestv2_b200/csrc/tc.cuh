@@ -41,6 +41,7 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+#pragma unroll 1        // (left to itself nvcc unrolls this spin 64x at every call site: ~2 KB of SASS each)
     for (uint32_t it = 0; it < (1u << 26); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
