@@ -164,6 +164,36 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def parity_check(model, x, preds, out, counts, c, dev, n=8):
+    """The bench's own weights and inputs against the oracle: six head tensors within 1e-4, decode within 1e-4, NMS rows
+    bit-exact on identical decoded input, fused decode+NMS identical to decode -> NMS.  Raises on a mismatch."""
+    import numpy as np
+    import yfv2_engine as eng
+    from oracle import net as onet, post as opost
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    xs = x[:n].cpu()
+    with torch.no_grad():
+        ref = onet.forward(sd, xs)
+    worst = 0.0
+    for i, (p_, r_) in enumerate(zip(preds, ref)):
+        a, b = p_[:n].cpu().numpy(), r_.numpy()
+        worst = max(worst, float(np.abs(a - b).max()))
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4, err_msg="bench parity: head tensor %d" % i)
+    p8 = [p_[:n].contiguous() for p_ in preds]
+    dets = eng.decode(p8, c)
+    np.testing.assert_allclose(dets.cpu().numpy(), opost.decode(ref, c).numpy(), rtol=1e-4, atol=1e-4, err_msg="bench parity: decode")
+    got, cnt, _ = eng.nms(dets, CONF, IOU, want_idx=False)
+    want = opost.nms(dets.cpu(), CONF, IOU)
+    for i, w_ in enumerate(want):
+        k = int(cnt[i])
+        if k != w_.shape[0] or not np.array_equal(got[i, :k].cpu().numpy(), w_.numpy()):
+            raise AssertionError("bench parity: NMS rows of image %d differ from the oracle" % i)
+        if int(counts[i]) != k or not torch.equal(out[i, :k], got[i, :k]):
+            raise AssertionError("bench parity: fused decode+NMS differs from decode -> NMS on image %d" % i)
+    return {"images": n, "max_abs_err_heads": worst, "tol": 1e-4, "nms": "bit-exact vs oracle on identical decoded input",
+            "fused_equals_unfused": True}
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import yfv2  # noqa: F401
@@ -219,6 +249,11 @@ def run_ours(args, rank, world, local_rank):
     value = world * BATCH * args.steps / (ms / 1e3)
     kept = int(counts.sum().item())
 
+    # ---- parity of THIS workload (outside the timed region): first images of the step against the CPU oracle ---------
+    parity = None
+    if rank == 0:
+        parity = parity_check(model, x, preds, out, counts, c, dev)
+
     # ---- e2e: pinned host uint8 in, pinned host detections out, double buffered on two streams ------------
     e2e = None
     try:
@@ -269,7 +304,7 @@ def run_ours(args, rank, world, local_rank):
     roof, stages = None, None
     if rank == 0:
         peak, peak_src = measured_peak()
-        bpi = algorithmic_bytes_per_image()
+        bpi = algorithmic_bytes_per_image(SIDE, SIDE)
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)       # 256 MB > L2
         reps = max(3, min(args.steps, 10))
         plan.forward(x, preds)
@@ -319,9 +354,13 @@ def run_ours(args, rank, world, local_rank):
         bb_bytes = sum(s["alg_MB"] for s in bb) * 1e6
         bb_us = sum(s["us"] for s in bb)
         traffic = None
-        try:        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                traffic = json.load(f)["per_launch_bytes"].get(top["stage"])
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:       # regenerate: tools/ncu_traffic.py
+                per = json.load(f)["per_launch_bytes"]
+            traffic = per.get(top["stage"])
+            for s_ in stages:
+                if per.get(s_["stage"]):
+                    s_["traffic_ratio"] = round(per[s_["stage"]] / (s_["alg_MB"] * 1e6), 3)
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": top["stage"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
@@ -337,14 +376,114 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": v, "unit": "images/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC if SIDE == 352 else "images/sec %dx%d fwd+decode+NMS" % (SIDE, SIDE), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "batch=256 352x352 inference (backbone+FPN+head+decode+NMS) per GPU, random weights, "
-                                       "NMS conf 0.001 iou 0.4", "global_batch": world * BATCH, "parallelism": "replicas x%d, no collective" % world,
-                           "l2": "inputs (380 MB fp32 per step) exceed the 126 MB L2; activations stream through it"},
+                "config": {"workload": "batch=%d %dx%d inference (backbone+FPN+head+decode+NMS) per GPU, random weights, "
+                                       "NMS conf 0.001 iou 0.4" % (BATCH, SIDE, SIDE), "global_batch": world * BATCH,
+                           "parallelism": "replicas x%d, no collective" % world,
+                           "l2": "inputs (%d MB fp32 per step) exceed the 126 MB L2; activations stream through it" % (BATCH * 3 * SIDE * SIDE * 4 // 1000000)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (plan.forward_launches + 1),
-                "kept_boxes_per_step": kept, "roofline": roof, "cpu_baseline": cpu, "stages": stages}
+                "kept_boxes_per_step": kept, "parity_checked": parity is not None, "parity": parity, "roofline": roof, "cpu_baseline": cpu, "stages": stages}
+        print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_train(args, rank, world, local_rank):
+    """BASELINE configs[2]: train.py loop on synthetic boxes, batch 64 per GPU (512 on 8), forward (batch-statistics BN) ->
+    DetectorLoss -> backward -> ONE NCCL all-reduce of the flat 243 095-float gradient bucket -> SGD.  Weak scaling."""
+    import yfv2  # noqa: F401
+    import synth
+    import model.detector as det
+    import utils.loss as ul
+    import train_ddp
+    TB = 64
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(2)                                                 # same initial weights on every rank
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        m = det.Detector(CLASSES, ANCHORS, True).to(dev).train()
+    bucket = train_ddp.FlatGradBucket(m.parameters())
+    opt = train_ddp.make_optimizer(m, 1e-3)
+    c = cfg()
+    g = torch.Generator().manual_seed(2 + rank)
+    x = torch.rand(TB, 3, SIDE, SIDE, generator=g).to(dev)               # the rank's shard of the 512-image batch
+    targets = synth.make_targets(2 + rank, TB).to(dev)                   # ~7 boxes per image (SURVEY 8d config[2])
+    xh = (torch.rand(TB, 3, SIDE, SIDE, generator=g) * 255).to(torch.uint8).pin_memory()
+    th = synth.make_targets(20 + rank, TB).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        return train_ddp.train_step(m, bucket, opt, x, targets, c, ul.compute_loss)
+
+    def e2e_step():
+        xi = xh.to(dev, non_blocking=True).float() / 255.0               # train.py:101
+        ti = th.to(dev, non_blocking=True)
+        losses = train_ddp.train_step(m, bucket, opt, xi, ti, c, ul.compute_loss)
+        return float(losses[3].detach())                                          # the loss read the reference's progress bar does every iteration
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        losses = step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    # the collective alone (device time, max over ranks)
+    ar = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(stream)
+        bucket.allreduce_mean()
+        b.record(stream)
+        b.synchronize()
+        ar.append(a.elapsed_time(b) * 1e3)
+    ar_us = torch.tensor([sorted(ar)[len(ar) // 2]], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ar_us, op=torch.distributed.ReduceOp.MAX)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(args.steps):
+        last = e2e_step()
+    s1.record(stream)
+    barrier()
+    t2 = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": "training images/sec 352x352 fwd+loss+bwd+allreduce+SGD", "mode": "train", "value": world * TB * args.steps / (ms / 1e3),
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "train.py loop, batch 64 per GPU (global %d) @352x352, synthetic boxes (1..13 per image), DetectorLoss "
+                                       "backward, one NCCL all-reduce of the flat gradient bucket, SGD(momentum 0.949, wd 5e-4); default PyTorch init "
+                                       "(the pretrained backbone.pth is not on the GPU box)" % (world * TB),
+                           "global_batch": world * TB, "parallelism": "dp%d" % world},
+                "clocks": clocks, "loss": float(losses[3].detach()),
+                "allreduce": {"us": float(ar_us.item()), "bytes": bucket.flat.numel() * 4, "comm_nranks": world,
+                              "collectives_per_step": 1 if world > 1 else 0},
+                "e2e": {"value": world * TB * args.steps / (float(t2.item()) / 1e3), "unit": "images/s",
+                        "h2d_bytes_per_step": xh.numel() + th.numel() * 4, "d2h_bytes_per_step": 4,
+                        "api": "train_ddp.train_step from pinned host uint8 images + targets, loss read back every step", "last_loss": last}}
         print(json.dumps(line), flush=True)
 
 
@@ -354,10 +493,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=352, help="input height = width (640: BASELINE configs[3], 256 images per GPU)")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="infer: BASELINE configs[1] (default); train: configs[2]")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    globals().update(SIDE=args.side, BATCH=args.batch)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -367,7 +510,10 @@ def main():
         torch.cuda.set_device(local_rank)
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.mode == "train":
+            run_train(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             torch.distributed.destroy_process_group()

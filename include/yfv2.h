@@ -60,6 +60,11 @@ YFV2_API const char* yfv2_last_error(void);
 YFV2_API int yfv2_plan_create(yfv2_plan** plan, int device, int N, int H, int W, int A, int C, int training);
 YFV2_API int yfv2_plan_destroy(yfv2_plan* plan);
 YFV2_API int yfv2_plan_workspace_bytes(const yfv2_plan* plan, size_t* bytes);
+/* The workspace is caller-owned but DEDICATED to the plan while the plan is in use: activation planes live in it inside
+ * zero frames (the padding of every 3x3 / 5x5 convolution) which the first forward on a given workspace pointer writes
+ * once and later forwards rely on.  If the memory was used for anything else in between, or was freed and re-allocated
+ * (a caching allocator may hand back the same address), call yfv2_plan_invalidate_workspace() before the next forward. */
+YFV2_API int yfv2_plan_invalidate_workspace(yfv2_plan* plan);
 YFV2_API int yfv2_plan_packed_bytes(const yfv2_plan* plan, size_t* bytes);
 /* number of kernels one yfv2_forward / yfv2_detect launches (for bench.py's gpu_launches) */
 YFV2_API int yfv2_plan_forward_launches(const yfv2_plan* plan, int* n);
@@ -112,6 +117,14 @@ YFV2_API int yfv2_decode_nms(const float* const preds[6], int N, int H, int W, i
                     const double* anchors_host, float conf_thres, double iou_thres,
                     const int* class_filter, int n_filter, int max_det, float max_wh,
                     float* out, int* counts, int* kept_idx, void* workspace, void* stream);
+
+/* ---- get_batch_statistics (utils/utils.py:184-230): true-positive flags of NMS output rows ----------------
+ * dets [N,max_det,6] / counts [N] as yfv2_nms writes them; targets [nt,6] rows (image, class, x1, y1, x2, y2) in
+ * pixels (what evaluation() builds at utils/utils.py:372-375), nt <= 8192.  tp [N,max_det] receives 1.0 for a true
+ * positive, 0.0 otherwise (rows past counts[n] are 0).  Same greedy order and the same fp32 IoU (+1 convention) as the
+ * reference: bit-identical flags. */
+YFV2_API int yfv2_batch_statistics(const float* dets, const int* counts, int N, int max_det, const float* targets, int nt,
+                                   float iou_threshold, float* tp, void* stream);
 
 /* ---- whole inference step with HOST buffers (the evaluation() inner loop, utils/utils.py:367-383) ----
  * x_host: pinned uint8 [N,3,H,W]; out_host: pinned [N,max_det,6]; counts_host: pinned [N].

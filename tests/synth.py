@@ -108,3 +108,36 @@ NMS_CASES = {
     "lowobj":   dict(seed=56, n=2, m=1815, obj_pow=3.0, classes=80, side=352.0),
     "c20":      dict(seed=57, n=2, m=1500, classes=20),
 }
+
+
+def make_eval_case(seed, n_img, max_det=40, max_gt=9, classes=6, size=352):
+    """Seeded NMS-like outputs and pixel-xyxy targets for the evaluation bookkeeping tests: per image a list of boxes by
+    descending confidence (some are jittered copies of ground-truth boxes, some have a wrong label, some are noise), and
+    targets rows (image, class, x1, y1, x2, y2).  Returns (list of [n_i,6] float32 arrays, targets [nt,6] float32)."""
+    rs = np.random.RandomState(seed)
+    outs, tg = [], []
+    for i in range(n_img):
+        ng = rs.randint(0, max_gt + 1)
+        gt = np.zeros((ng, 6), np.float32)
+        gt[:, 0] = i
+        gt[:, 1] = rs.randint(0, classes, ng)
+        c = rs.rand(ng, 2) * size
+        wh = 8 + rs.rand(ng, 2) * size * 0.4
+        gt[:, 2:4], gt[:, 4:6] = c - wh / 2, c + wh / 2
+        tg.append(gt)
+        nd = rs.randint(0, max_det + 1)
+        d = np.zeros((nd, 6), np.float32)
+        for j in range(nd):
+            kind = rs.rand()
+            if ng and kind < 0.6:                      # a detection of some ground-truth box, jittered
+                g = gt[rs.randint(ng)]
+                d[j, :4] = g[2:6] + rs.randn(4) * (3 if kind < 0.4 else 40)
+                d[j, 5] = g[1] if rs.rand() < 0.8 else rs.randint(0, classes)
+            else:
+                c2 = rs.rand(2) * size
+                wh2 = 8 + rs.rand(2) * size * 0.4
+                d[j, :2], d[j, 2:4] = c2 - wh2 / 2, c2 + wh2 / 2
+                d[j, 5] = rs.randint(0, classes + 2)
+        d[:, 4] = np.sort(rs.rand(nd).astype(np.float32))[::-1]
+        outs.append(d)
+    return outs, np.concatenate(tg, 0) if tg else np.zeros((0, 6), np.float32)

@@ -349,6 +349,349 @@ s1c_kernel(const __grid_constant__ S1cArgs p) {
     if (warp == 0) tmem_dealloc(tmem_slot, 512);
 }
 
+// depthwise 3x3 (column stride S between taps' source pixels is 1: the taps are r[0], r[1], r[2] of three window rows) + BN
+// for one channel of one output pixel; row-major staged planes.  Same association as k_tcnet.cu's dw8p (bit-identical).
+template <int S>
+__device__ __forceinline__ float dw3(const float* __restrict__ r0, const float* __restrict__ r1, const float* __restrict__ r2,
+                                     const float* __restrict__ wk) {
+    const float4 wa = *reinterpret_cast<const float4*>(wk);
+    const float4 wb = *reinterpret_cast<const float4*>(wk + 4);
+    const float4 wc = *reinterpret_cast<const float4*>(wk + 8);
+    float p0 = wa.x * r0[0]; p0 = fmaf(wa.y, r0[1], p0); p0 = fmaf(wa.z, r0[2], p0);
+    float p1 = wa.w * r1[0]; p1 = fmaf(wb.x, r1[1], p1); p1 = fmaf(wb.y, r1[2], p1);
+    float p2 = wb.z * r2[0]; p2 = fmaf(wb.w, r2[1], p2); p2 = fmaf(wc.x, r2[2], p2);
+    const float d = (p0 + p1) + p2;
+    return fmaf(d, wc.y, wc.z);
+}
+
+// ===================================================================================================
+// s2c_kernel: stride-2 ShuffleV2 block (reference shufflenetv2.py:34-44,52-55), K = 24 / 48 channels per branch.
+//   proj:  dw3x3 s2 + BN on the raw input -> pw + BN + ReLU             -> output planes [0, K)
+//   main:  pw1 + BN + ReLU (full resolution) -> dw3x3 s2 + BN -> pw2 + BN + ReLU -> output planes [K, 2K)
+// The round-1 kernel ran proj / pw1 / main as three CTA-wide phases per band with one staging buffer: ncu showed 70 % of the
+// warp samples waiting (21 % on the TMA load of the band, 30 % at the phase barriers where 1 of 4 groups had a tile, 18 % on
+// MMA completion).  Here a band X_i (2 TR + 1 framed input rows of the K planes, one TMA bulk copy per plane) is double
+// buffered by a producer warp, pw1 runs IN PLACE in X_i, and the item loop is skewed so that both phases keep every
+// warpgroup busy:
+//     phase B(i):    pw1 on the in-image pixels of X_i                          (many tiles, all groups)
+//     phase M+P(i):  main(i) tiles on T_i = X_i  and  proj(i+1) tiles on the raw X_(i+1), side by side
+// ===================================================================================================
+struct S2cArgs {
+    Planes in, out;
+    uint32_t in_off[kMaxK];                 // plane offsets (floats) of the K input channels
+    uint32_t out_off[2 * kMaxK];            // and of the 2K output channels (proj first)
+    const float* wp; const float* w1; const float* w2;      // tc packs
+    const float* wdwp; const float* wdwm;                   // dw3 packs
+    int N, TR, bandsPerImg;
+};
+
+template <int K, int NP, int G, int KC, int NB>
+__global__ void __launch_bounds__(G * 128 + 32, 1)
+s2c_kernel(const __grid_constant__ S2cArgs p) {
+    pdl_trigger();
+    constexpr int KP = K, NCH = K / KC;
+    constexpr int COLS = NB * 2 * KC + NP, DCOL = NB * 2 * KC;
+    static_assert(G * COLS <= 512 && K % KC == 0 && KC % 8 == 0 && NP % 16 == 0 && K <= kMaxK, "shape");
+    constexpr int WFL = 2 * NP * KP + 2 * NP;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) BPipe pipes[G];
+    __shared__ __align__(8) uint64_t wbar, xfull[2], xfree[2];
+    __shared__ uint32_t tmem_slot;
+    float* sBp = smem;
+    float* sB1 = sBp + WFL;
+    float* sB2 = sB1 + WFL;
+    float* sDWp = sB2 + WFL;
+    float* sDWm = sDWp + K * 12;
+    float* Xb = sDWm + K * 12;
+    const int Hin = p.in.H, Win = p.in.W, WS = p.in.Ws, pin = p.in.pad;
+    const int Hout = p.out.H, Wout = p.out.W;
+    const int XR = 2 * p.TR + 1;                            // staged rows per band
+    const int RS = XR * WS;                                 // plane stride inside a staging buffer
+    const int XBUF = K * RS;
+    const int warp = threadIdx.x >> 5;
+    const int items = p.N * p.bandsPerImg;
+    const int my_items = ((int)blockIdx.x < items) ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&wbar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xfree[i], G * 4); }
+        for (int i = 0; i < G; ++i) {
+            mbar_init(&pipes[i].empty[0], 1); mbar_init(&pipes[i].empty[1], 1); mbar_init(&pipes[i].dfull, 1);
+            pipes[i].arrivals[0] = 0; pipes[i].arrivals[1] = 0;
+        }
+        fence_mbar_init();
+        mbar_expect_tx(&wbar, (uint32_t)((3 * WFL + 2 * K * 12) * sizeof(float)));
+        bulk_g2s(sBp, p.wp, WFL * sizeof(float), &wbar);
+        bulk_g2s(sB1, p.w1, WFL * sizeof(float), &wbar);
+        bulk_g2s(sB2, p.w2, WFL * sizeof(float), &wbar);
+        bulk_g2s(sDWp, p.wdwp, K * 12 * sizeof(float), &wbar);
+        bulk_g2s(sDWm, p.wdwm, K * 12 * sizeof(float), &wbar);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    pdl_wait();                                             // predecessor's activations are complete and visible from here on
+
+    auto item_geom = [&](int it, int& n, int& r0, int& rows) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        n = item / p.bandsPerImg;
+        r0 = (item - n * p.bandsPerImg) * p.TR;
+        rows = min(p.TR, Hout - r0);
+    };
+
+    if (warp == G * 4) {
+        // ---------------- producer: band it -> buffer it & 1 -------------------------------------------------------
+        const int lane = threadIdx.x & 31;
+        for (int it = 0; it < my_items; ++it) {
+            const int buf = it & 1;
+            int n, r0, rows;
+            item_geom(it, n, r0, rows);
+            const int nrows = 2 * rows + 1;
+            if (it >= 2) mbar_wait(&xfree[buf], (uint32_t)((it >> 1) - 1) & 1u);     // every compute warp is done with the buffer
+            publish_async();
+            if (lane == 0) mbar_expect_tx(&xfull[buf], (uint32_t)(K * nrows * WS * sizeof(float)));
+            __syncwarp();
+            const float* src0 = p.in.base + (long long)n * p.in.sN + (long long)(2 * r0 - 1 + pin) * WS;
+            for (int k = lane; k < K; k += 32)
+                bulk_g2s(Xb + (size_t)buf * XBUF + (size_t)k * RS, src0 + p.in_off[k], (uint32_t)(nrows * WS * sizeof(float)), &xfull[buf]);
+        }
+    } else {
+        // ---------------- compute warpgroups -----------------------------------------------------------------------
+        BGrp g;
+        const int grp = threadIdx.x >> 7;
+        g.tcol = tmem_slot + grp * COLS;
+        g.tlane = g.tcol + ((uint32_t)(32 * (warp & 3)) << 16);
+        g.pipe = &pipes[grp];
+        g.chunk = 0; g.dparity = 0;
+        g.gtid = threadIdx.x & 127;
+        const uint32_t bp_hi = smem_u32(sBp), bp_lo = smem_u32(sBp + NP * KP);
+        const uint32_t b1_hi = smem_u32(sB1), b1_lo = smem_u32(sB1 + NP * KP);
+        const uint32_t b2_hi = smem_u32(sB2), b2_lo = smem_u32(sB2 + NP * KP);
+        const float* affp = sBp + 2 * NP * KP;
+        const float* aff1 = sB1 + 2 * NP * KP;
+        const float* aff2 = sB2 + 2 * NP * KP;
+        mbar_wait(&wbar, 0);
+
+        // one 128-pixel tile of a depthwise-s2 -> pointwise branch of band (n, r0, rows) out of staging buffer X
+        auto dw_tile = [&](const float* X, int n, int r0, int rows, int tile, const float* sDW, uint32_t b_hi, uint32_t b_lo,
+                           const float* aff, const uint32_t* ooff) {
+            const int npix = rows * Wout;
+            const int q = tile * 128 + g.gtid;
+            const bool valid = q < npix;
+            const int qc = valid ? q : 0;
+            const int orow = qc / Wout, ox = qc - orow * Wout;
+            const float* w0 = X + (2 * orow) * WS + 2 * ox + (pin - 1);      // window's top-left (frame column pin-1 <-> input column -1)
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                float a[KC];
+                const float* t = w0 + c * KC * RS;
+                const float* wk = sDW + c * KC * 12;
+#pragma unroll
+                for (int j = 0; j < KC; ++j) {
+                    a[j] = dw3<2>(t, t + WS, t + 2 * WS, wk);
+                    t += RS; wk += 12;
+                }
+                st_acquire<NB>(g);
+                st_store<KC, NB>(g, a);
+                st_hand_off<KP, NP, KC, NB>(g, c, b_hi, b_lo, DCOL, c == NCH - 1);
+            }
+            st_wait_d(g);
+            float* op = p.out.base + (long long)n * p.out.sN + p.out.org + (r0 + orow) * p.out.Ws + ox;
+#pragma unroll
+            for (int n0 = 0; n0 < NP; n0 += 16) {
+                if (n0 >= K) break;
+                float d[16];
+                tmem_ld16v(g.tlane + DCOL + n0, d);
+                wait_ld();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < K) op[ooff[n0 + j]] = fmaxf(fmaf(d[j], aff[n0 + j], aff[NP + n0 + j]), 0.f);
+                }
+            }
+        };
+        auto proj_tiles = [&](int it, int first, int step) {          // proj tiles first, first+step, ... of band it
+            int n, r0, rows;
+            item_geom(it, n, r0, rows);
+            const float* X = Xb + (size_t)(it & 1) * XBUF;
+            for (int tile = first; tile * 128 < rows * Wout; tile += step)
+                dw_tile(X, n, r0, rows, tile, sDWp, bp_hi, bp_lo, affp, p.out_off);
+        };
+
+        if (my_items > 0) {
+            mbar_wait(&xfull[0], 0);
+            proj_tiles(0, grp, G);
+            group_bar(1, G * 128);                          // proj(0) has read the raw X_0: pw1 may overwrite it
+        }
+        for (int it = 0; it < my_items; ++it) {
+            int n, r0, rows;
+            item_geom(it, n, r0, rows);
+            float* X = Xb + (size_t)(it & 1) * XBUF;
+            const int gr0 = 2 * r0 - 1, nrows = 2 * rows + 1;     // input rows [gr0, gr0 + nrows) <-> staged rows [0, nrows)
+            // ---- phase B: pw1 + BN + ReLU in place on every staged in-image pixel (frame / halo positions stay zero) --------
+            const int gr_lo = max(gr0, 0), gr_hi = min(gr0 + nrows - 1, Hin - 1);
+            const int npos = (gr_hi - gr_lo + 1) * Win;
+            for (int tile = grp; tile * 128 < npos; tile += G) {
+                const int q = tile * 128 + g.gtid;
+                const bool valid = q < npos;
+                const int qc = valid ? q : 0;
+                const int rr = qc / Win, x = qc - rr * Win;
+                float* tpos = X + (gr_lo + rr - gr0) * WS + pin + x;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    float a[KC];
+#pragma unroll
+                    for (int j = 0; j < KC; ++j) a[j] = tpos[(c * KC + j) * RS];
+                    st_acquire<NB>(g);
+                    st_store<KC, NB>(g, a);
+                    st_hand_off<KP, NP, KC, NB>(g, c, b1_hi, b1_lo, DCOL, c == NCH - 1);
+                }
+                st_wait_d(g);
+#pragma unroll
+                for (int n0 = 0; n0 < NP; n0 += 16) {
+                    if (n0 >= K) break;
+                    float d[16];
+                    tmem_ld16v(g.tlane + DCOL + n0, d);
+                    wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < K) tpos[(n0 + j) * RS] = fmaxf(fmaf(d[j], aff1[n0 + j], aff1[NP + n0 + j]), 0.f);
+                    }
+                }
+            }
+            group_bar(1, G * 128);
+            // ---- phase M+P: main(it) out of T = X, proj(it + 1) out of the raw next band, side by side ---------------------
+            const int mt = (rows * Wout + 127) / 128;               // main tiles of this band
+            const bool more = it + 1 < my_items;
+            if (more) mbar_wait(&xfull[(it + 1) & 1], (uint32_t)((it + 1) >> 1) & 1u);
+            for (int job = grp; job < mt; job += G)
+                dw_tile(X, n, r0, rows, job, sDWm, b2_hi, b2_lo, aff2, p.out_off + K);
+            if (more) proj_tiles(it + 1, ((grp - mt) % G + G) % G, G);       // the groups after the main jobs take the first proj tiles
+            group_bar(1, G * 128);                          // X_it is fully consumed; proj(it + 1) has read the raw X_(it+1)
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&xfree[it & 1]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
+// ===================================================================================================
+// pw3_kernel: plain pointwise convolution over planes, out = ReLU(BN(W . in)), with gather-on-load: KA channels read through
+// (y >> SHA, x >> SHA) from pool A (the FPN's nearest-neighbour up-sampling of C3, reference model/fpn.py:57-58), then KB channels
+// at (y, x) from pool B.  Used by fpn.S2 (192 up-sampled + 96), fpn.S3 (192) and the pointwise-1 of the K = 96 stride-2 block.
+// One tile = 128 consecutive pixels of the flattened (image, pixel) space; a thread's K loads are software pipelined, the
+// next 16 channels are in flight while the current 16 are split and handed to the tensor core (round 1 issued 48 loads,
+// waited, then paid 6 hand-offs of 8 channels: six fully exposed load batches per 288-channel tile).
+// ===================================================================================================
+constexpr int kPwMaxK = 288;
+struct Pw3Args {
+    Planes A, B, out;
+    uint32_t in_off[kPwMaxK];          // plane offset (floats) of input channel k inside its pool
+    uint32_t out_off[96];
+    const float* wpack;                // tc pack: Bhi | Blo | scale | shift
+    int N, nout;
+};
+
+template <int KA, int KB, int SHA, int NP, int G, bool RELU>
+__global__ void __launch_bounds__(G * 128, 1)
+pw3_kernel(const __grid_constant__ Pw3Args p) {
+    pdl_trigger();
+    constexpr int KP = KA + KB, KC = 16, NB = 2, NCH = KP / KC;
+    constexpr int COLS = NB * 2 * KC + NP;
+    static_assert(G * COLS <= 512 && KP % (2 * KC) == 0 && KA % KC == 0 && NP % 16 == 0 && KP <= kPwMaxK, "shape");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) BPipe pipes[G];
+    __shared__ __align__(8) uint64_t wbar;
+    __shared__ uint32_t tmem_slot;
+    float* sB = smem;
+    constexpr int WFL = 2 * NP * KP + 2 * NP;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 32) {
+        mbar_init(&wbar, 1);
+        for (int i = 0; i < G; ++i) {
+            mbar_init(&pipes[i].empty[0], 1); mbar_init(&pipes[i].empty[1], 1); mbar_init(&pipes[i].dfull, 1);
+            pipes[i].arrivals[0] = 0; pipes[i].arrivals[1] = 0;
+        }
+        fence_mbar_init();
+        mbar_expect_tx(&wbar, (uint32_t)(WFL * sizeof(float)));
+        constexpr uint32_t kPiece = 32768;                 // a bulk copy carries at most 2^20-1 bytes; keep the pieces modest
+        for (uint32_t o = 0; o < WFL * sizeof(float); o += kPiece)
+            bulk_g2s(reinterpret_cast<char*>(sB) + o, reinterpret_cast<const char*>(p.wpack) + o,
+                     min(kPiece, (uint32_t)(WFL * sizeof(float)) - o), &wbar);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    BGrp g;
+    const int grp = threadIdx.x >> 7;
+    g.tcol = tmem_slot + grp * COLS;
+    g.tlane = g.tcol + ((uint32_t)(32 * (warp & 3)) << 16);
+    g.pipe = &pipes[grp];
+    g.chunk = 0; g.dparity = 0;
+    g.gtid = threadIdx.x & 127;
+    const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * KP);
+    const float* aff = sB + 2 * NP * KP;
+    const int HW = p.out.H * p.out.W, W = p.out.W;
+    const long long total = (long long)p.N * HW;
+    const int ntiles = (int)((total + 127) / 128);
+    pdl_wait();                                            // predecessor's activations are complete and visible from here on
+    mbar_wait(&wbar, 0);
+    for (int tile = blockIdx.x * G + grp; tile < ntiles; tile += gridDim.x * G) {
+        const long long pos = (long long)tile * 128 + g.gtid;
+        const bool valid = pos < total;
+        const long long pc = valid ? pos : 0;              // lanes past the end recompute pixel 0 and drop the result
+        const int n = (int)(pc / HW);
+        const int px = (int)(pc - (long long)n * HW);
+        const int y = px / W, x = px - y * W;
+        const float* baseA = p.A.base + (long long)n * p.A.sN + p.A.org + (y >> SHA) * p.A.Ws + (x >> SHA);
+        const float* baseB = p.B.base + (long long)n * p.B.sN + p.B.org + y * p.B.Ws + x;
+        float v[2][KC];
+        auto load = [&](int c, float* dst) {               // c is a multiple-of-KC chunk index; chunks never straddle the A / B split
+            const float* base = (c * KC < KA) ? baseA : baseB;
+#pragma unroll
+            for (int j = 0; j < KC; ++j) dst[j] = __ldcg(base + p.in_off[c * KC + j]);
+        };
+        load(0, v[0]);
+#pragma unroll 1
+        for (int c = 0; c < NCH; c += 2) {
+            load(c + 1, v[1]);
+            st_acquire<NB>(g);
+            st_store<KC, NB>(g, v[0]);
+            st_hand_off<KP, NP, KC, NB>(g, c, b_hi, b_lo, NB * 2 * KC, false);
+            if (c + 2 < NCH) load(c + 2, v[0]);
+            st_acquire<NB>(g);
+            st_store<KC, NB>(g, v[1]);
+            st_hand_off<KP, NP, KC, NB>(g, c + 1, b_hi, b_lo, NB * 2 * KC, c + 2 == NCH);
+        }
+        st_wait_d(g);
+        float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + y * p.out.Ws + x;
+#pragma unroll
+        for (int n0 = 0; n0 < NP; n0 += 16) {
+            float d[16];
+            tmem_ld16v(g.tlane + NB * 2 * KC + n0, d);
+            wait_ld();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int nn = n0 + j;
+                    if (nn < p.nout) {
+                        float r = fmaf(d[j], aff[nn], aff[NP + nn]);
+                        if (RELU) r = fmaxf(r, 0.f);
+                        obase[p.out_off[nn]] = r;
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_slot, 512);
+}
+
 template <typename Kern>
 int blk_smem_attr(Kern kern, size_t bytes) {
     if (bytes > kSmemCap) { set_error("block kernel needs %zu bytes of shared memory", bytes); return YFV2_EUNSUPPORTED; }
@@ -415,6 +758,59 @@ int blk_launch_s1(int K, const Planes& P, int nblk, const ChanTab* tin, const Ch
     *done = nblk;
     if (K == 24) return run(s1c_kernel<24, 32, 4, 8, 2>, 4);
     return run(s1c_kernel<48, 48, 2, 16, 2>, 2);
+}
+
+// Stride-2 block of branch width K (24 or 48): in (K planes at 2H x 2W) -> out (2K planes at H x W).
+int blk_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin, const ChanTab& tout, const float* wdwp, const float* wp,
+                  const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s) {
+    if (K != 24 && K != 48) { set_error("blk_launch_s2: unsupported K=%d", K); return YFV2_EUNSUPPORTED; }
+    S2cArgs a{};
+    a.in = in; a.out = out; a.wp = wp; a.w1 = w1; a.w2 = w2; a.wdwp = wdwp; a.wdwm = wdwm; a.N = N;
+    for (int k = 0; k < K; ++k) a.in_off[k] = (uint32_t)((long long)tin.c[k] * in.sC);
+    for (int k = 0; k < 2 * K; ++k) a.out_off[k] = (uint32_t)((long long)tout.c[k] * out.sC);
+    const int NP = tc_round(K, 16);
+    const size_t wfl = (size_t)3 * (2 * NP * K + 2 * NP) + 2 * K * 12;
+    auto bytes = [&](int tr) { return (wfl + (size_t)2 * K * (2 * tr + 1) * in.Ws) * sizeof(float); };
+    int TR = out.H;
+    while (TR > 1 && bytes(TR) > kBlkSmemBudget) --TR;
+    if (bytes(TR) > kBlkSmemBudget) { set_error("blk_launch_s2: a %dx%d input does not fit in shared memory", in.H, in.W); return YFV2_EUNSUPPORTED; }
+    const int bands = (out.H + TR - 1) / TR;
+    TR = (out.H + bands - 1) / bands;                        // equalise the bands
+    a.TR = TR; a.bandsPerImg = (out.H + TR - 1) / TR;
+    const int items = N * a.bandsPerImg;
+    auto run = [&](auto kern, int G) -> int {
+        TRYB(blk_smem_attr(kern, bytes(TR)));
+        YFV2_CUDA(launch_k(kern, min(items, sm_count()), G * 128 + 32, bytes(TR), s, pdl_take(), a));
+        YFV2_LAUNCH_CHECK();
+        return YFV2_OK;
+    };
+    if (K == 24) return run(s2c_kernel<24, 32, 4, 24, 1>, 4);
+    return run(s2c_kernel<48, 48, 4, 16, 2>, 4);
+}
+
+// plain pointwise; kind 0: 96->96 (+ReLU)  1: FPN S3 192->72 (+ReLU)  2: FPN S2 (up(192) ++ 96)->72 (+ReLU)
+int blk_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, const ChanTab& tb, const Planes& out, const ChanTab& tout,
+                  const float* wpack, int N, cudaStream_t s) {
+    Pw3Args a{};
+    a.A = A; a.B = B; a.out = out; a.wpack = wpack; a.N = N;
+    const long long total = (long long)N * out.H * out.W;
+    const int ntiles = (int)((total + 127) / 128);
+    auto run = [&](auto kern, int KA, int KB, int NP, int G, int nout) -> int {
+        a.nout = nout;
+        for (int k = 0; k < KA; ++k) a.in_off[k] = (uint32_t)((long long)ta.c[k] * A.sC);
+        for (int k = 0; k < KB; ++k) a.in_off[KA + k] = (uint32_t)((long long)tb.c[k] * B.sC);
+        for (int k = 0; k < nout; ++k) a.out_off[k] = (uint32_t)((long long)tout.c[k] * out.sC);
+        const size_t bytes = (size_t)(2 * NP * (KA + KB) + 2 * NP) * sizeof(float);
+        TRYB(blk_smem_attr(kern, bytes));
+        YFV2_CUDA(launch_k(kern, min((ntiles + G - 1) / G, sm_count()), G * 128, bytes, s, pdl_take(), a));
+        YFV2_LAUNCH_CHECK();
+        return YFV2_OK;
+    };
+    if (kind == 0) return run(pw3_kernel<96, 0, 0, 96, 3, true>, 96, 0, 96, 3, 96);
+    if (kind == 1) return run(pw3_kernel<192, 0, 0, 80, 3, true>, 192, 0, 80, 3, 72);
+    if (kind == 2) return run(pw3_kernel<192, 96, 1, 80, 3, true>, 192, 96, 80, 3, 72);
+    set_error("blk_launch_pw: unknown kind %d", kind);
+    return YFV2_EUNSUPPORTED;
 }
 
 }  // namespace yfv2

@@ -190,7 +190,6 @@ struct yfv2_plan {
     ChanTab logical[kNumBlocks];       // logical channel order of each block's output (debug gather)
     int launches;
     // tensor-core engine
-    int engine;                        // 0 = FFMA kernels (k_shuffle/k_fpn/k_head), 1 = tcgen05 kernels (k_tcnet)
     size_t tk_blk[kNumBlocks][3];      // tc packs per block: [0]=pw1 [1]=pw2 [2]=proj pw (stride-2 only)
     size_t tk_stem, tk_fpn3, tk_fpn2, tk_head[4][2], tk_out_oc, tk_out_reg;
     size_t tk_fold[4], pk_foldw[4];    // heads' second pointwise + BN + output conv folded into one matrix (tc pack / fp32 scratch)
@@ -324,7 +323,6 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     p->pk_floats = pk;
     for (int i = 0; i < 96; ++i) p->t96.c[i] = 0;   // filled per use (pool-specific offset)
 
-    p->engine = 1;
     if (A + C > 96 || 4 * A > 96) {
         set_error("plan_create: anchors+classes = %d exceeds the 96-wide output-conv tile of this build", A + C);
         delete p;
@@ -379,6 +377,12 @@ extern "C" int yfv2_plan_packed_bytes(const yfv2_plan* p, size_t* bytes) {
 extern "C" const char* yfv2_plan_stage_name(const yfv2_plan* p, int i) {
     if (!p || i < 0 || i >= p->n_stages) return nullptr;
     return p->stages[i].name;
+}
+
+extern "C" int yfv2_plan_invalidate_workspace(yfv2_plan* p) {
+    if (!p) { set_error("invalidate_workspace: null plan"); return YFV2_EINVAL; }
+    p->ws_zeroed = nullptr;          // the next forward re-zeroes the frames around every activation plane
+    return YFV2_OK;
 }
 
 extern "C" int yfv2_plan_stage_group(const yfv2_plan* p, int i) {
@@ -530,6 +534,10 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
 bool blk_s1_chainable(int K, int H, int W);
 int blk_launch_s1(int K, const Planes& P, int nblk, const ChanTab* tin, const ChanTab* tout, const float* const* w1,
                   const float* const* wdw, const float* const* w2, int N, cudaStream_t s, int* done);
+int blk_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin, const ChanTab& tout, const float* wdwp, const float* wp,
+                  const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s);
+int blk_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, const ChanTab& tb, const Planes& out, const ChanTab& tout,
+                  const float* wpack, int N, cudaStream_t s);
 // k_tail.cu
 int tail_launch_s1(const Planes& P, int nblk, const ChanTab* tin, const ChanTab* tout, const float* const* w1,
                    const float* const* wdw, const float* const* w2, int N, cudaStream_t s, int* done);
@@ -563,7 +571,8 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
         const int b = st.a;
         switch (st.kind) {
         case 0: {
-            if (!getenv("YFV2_STEM_TC")) {   // default: register-tiled FFMA direct convolution (k_stem.cu explains why)
+            static const bool stem_tc = getenv("YFV2_STEM_TC") != nullptr;
+            if (!stem_tc) {   // default: register-tiled FFMA direct convolution (k_stem.cu explains why)
                 StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
                 TRY(launch_stem(a, s));
             } else {
@@ -612,8 +621,10 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             const int K = p->blk_K[b];
             const float* d = pk + p->pk_block[b];
             const int dwn = dw3_pack_floats(K), pwn = pw_pack_floats(K, K);
-            TRY(tc_launch_s2(K, pool_planes(p, ws, p->blk_res[b] - 1), pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b],
-                             d, pk + p->tk_blk[b][2], pk + p->tk_blk[b][0], d + dwn + 2 * pwn, pk + p->tk_blk[b][1], p->N, s));
+            static const bool old_s2 = getenv("YFV2_S2_OLD") != nullptr;          // round-1 kernel, kept for A/B runs
+            auto s2 = old_s2 ? tc_launch_s2 : blk_launch_s2;
+            TRY(s2(K, pool_planes(p, ws, p->blk_res[b] - 1), pool_planes(p, ws, p->blk_res[b]), p->tin[b], p->tout[b],
+                   d, pk + p->tk_blk[b][2], pk + p->tk_blk[b][0], d + dwn + 2 * pwn, pk + p->tk_blk[b][1], p->N, s));
         } break;
         case 16: {   // K=96 stride-1 blocks on a map of at most 128 pixels: one chained launch (k_tail.cu)
             int nb = 1;
@@ -636,8 +647,10 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             ChanTab t96;
             const int base = stride == 2 ? 144 : 288;           // scratch planes live in the INPUT resolution's pool
             for (int i = 0; i < 96; ++i) t96.c[i] = (unsigned short)(base + i);
+            static const bool old_pw = getenv("YFV2_PW_OLD") != nullptr;          // round-1 pointwise kernel, kept for A/B runs
             if (st.kind == 12) {
-                TRY(tc_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s));
+                if (old_pw) { TRY(tc_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s)); }
+                else { TRY(blk_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s)); }
             } else {
                 const float* d = pk + p->pk_block[b];
                 const int dwn = dw3_pack_floats(96), pwn = pw_pack_floats(96, 96);
@@ -656,8 +669,10 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             }
         } break;
         case 14: {   // tc FPN reducers
-            if (st.a == 1) { TRY(tc_launch_pw(1, f.c3, f.t3, f.c3, f.t3, f.s3, ident, pk + p->tk_fpn3, p->N, s)); }
-            else { TRY(tc_launch_pw(2, f.c3, f.t3, f.c2, f.t2, f.s2, ident, pk + p->tk_fpn2, p->N, s)); }
+            static const bool old_pw = getenv("YFV2_PW_OLD") != nullptr;
+            auto pw = old_pw ? tc_launch_pw : blk_launch_pw;
+            if (st.a == 1) { TRY(pw(1, f.c3, f.t3, f.c3, f.t3, f.s3, ident, pk + p->tk_fpn3, p->N, s)); }
+            else { TRY(pw(2, f.c3, f.t3, f.c2, f.t2, f.s2, ident, pk + p->tk_fpn2, p->N, s)); }
         } break;
         default: set_error("forward: unknown stage kind %d", st.kind); return YFV2_EINVAL;
         }

@@ -2,7 +2,7 @@
 model/backbone/shufflenetv2.py:5-114 module tree, so state_dict keys/shapes are identical:
 first_conv.{0,1}, stage{2,3,4}.{i}.branch_main.{0,1,3,4,5,6}, .branch_proj.{0,1,2,3}).
 
-These modules own weights only.  The arithmetic runs in libyfv2.so (csrc/k_stem.cu, k_shuffle.cu),
+These modules own weights only.  The arithmetic runs in libyfv2.so (csrc/k_stem.cu: stem + max-pool; k_blk.cu / k_tail.cu: chained stride-1 blocks; k_tcnet.cu: stride-2 blocks),
 dispatched from Detector.forward; calling a sub-module directly is not supported."""
 import os
 

@@ -32,6 +32,7 @@ class Detector(nn.Module):
         self.output_obj_layers = nn.Conv2d(out_depth, anchor_num, 1, 1, 0, bias=True)
         self.output_cls_layers = nn.Conv2d(out_depth, classes, 1, 1, 0, bias=True)
         self._plans = {}
+        self._weights_gen = 0           # bumped whenever weights / BN buffers may have changed behind autograd's back
 
     # ---- weight bookkeeping ---------------------------------------------------------------------------
     def _weight_tensors(self):
@@ -41,6 +42,31 @@ class Detector(nn.Module):
             if isinstance(m, nn.BatchNorm2d):
                 bn += [m.running_mean, m.running_var]
         return params, bn
+
+    def invalidate_packed(self):
+        """Forces the next eval forward to re-fold BN and re-pack the weights.  Needed after edits that do not bump
+        `tensor._version` (`p.data.add_()`, raw-pointer updates); `forward()` in train mode and `load_state_dict` call it."""
+        self._weights_gen += 1
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_packed()
+        return r
+
+    # plans hold ctypes handles and device buffers: copies / pickles of the module start without them and re-pack lazily
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_plans" else copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_plans"] = {}
+        return st
 
     def _plan_for(self, x):
         N, _, H, W = x.shape
@@ -52,7 +78,7 @@ class Detector(nn.Module):
             plan = yfv2_engine.Plan(x.device, N, H, W, self.anchor_num, self.classes, training=False)
             self._plans[key] = plan
         params, bn = self._weight_tensors()
-        version = tuple(t._version for t in params + bn) + tuple(t.data_ptr() for t in params[:1])
+        version = (self._weights_gen,) + tuple(t._version for t in params + bn) + tuple(t.data_ptr() for t in params[:1])
         if plan.packed_version != version:
             plan.pack(params, bn)
             plan.packed_version = version
@@ -66,6 +92,7 @@ class Detector(nn.Module):
             if self.export_onnx:
                 raise NotImplementedError("export_onnx=True is an inference-only head")
             from model import train_ops
+            self.invalidate_packed()                      # the BN running statistics are updated through raw pointers
             return train_ops.forward_train(self, x.float() if x.dtype != torch.float32 else x)
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected input [N,3,H,W]")

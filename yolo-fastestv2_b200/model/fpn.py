@@ -1,5 +1,5 @@
 """Parameter containers for LightFPN and its DWConvblock heads (mirror of reference model/fpn.py:5-64:
-conv1x1_{2,3}.{0,1}, {cls,reg}_head_{2,3}.block.{0,1,3,4,5,6,8,9}).  Compute: csrc/k_fpn.cu, k_head.cu."""
+conv1x1_{2,3}.{0,1}, {cls,reg}_head_{2,3}.block.{0,1,3,4,5,6,8,9}).  Compute: csrc/k_tcnet.cu (tc_pw_kernel: FPN reducers; tc_head*_kernel: DWConvblock heads + folded output convs)."""
 import torch.nn as nn
 
 from model.backbone.shufflenetv2 import _WeightsOnly, _conv_bn

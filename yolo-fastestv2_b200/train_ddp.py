@@ -22,7 +22,22 @@ class FlatGradBucket:
     def zero(self):
         self.flat.zero_()
 
+    def reattach(self):
+        """`optimizer.zero_grad()` defaults to set_to_none=True since torch 2.0, which drops the views into the bucket (the
+        next backward then allocates fresh .grad tensors and the all-reduce would see zeros).  Re-point every .grad at its
+        slice, copying a gradient that was accumulated elsewhere."""
+        off = 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            off += p.numel()
+
     def allreduce_mean(self, group=None):
+        self.reattach()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)      # the single collective of the step
             self.flat.div_(dist.get_world_size(group))
@@ -33,12 +48,19 @@ def make_optimizer(model, lr):
     return torch.optim.SGD(params=model.parameters(), lr=lr, momentum=0.949, weight_decay=0.0005)    # train.py:81-85
 
 
-def train_step(model, bucket, optimizer, imgs, targets, cfg, compute_loss, group=None):
-    """forward (train mode) -> compute_loss -> backward -> one all-reduce -> SGD step.  Returns the 4 loss tensors."""
-    bucket.zero()
+def train_step(model, bucket, optimizer, imgs, targets, cfg, compute_loss, group=None, accumulate=False, step=True):
+    """forward (train mode) -> compute_loss -> backward -> one all-reduce -> SGD step.  Returns the 4 loss tensors.
+
+    accumulate=True keeps the gradients already in the bucket (the reference's `subdivisions`, train.py:122-124: several
+    backward passes per optimizer step); step=False skips the all-reduce and the optimizer step (all but the last
+    sub-batch).  Do not call `optimizer.zero_grad()` between steps: the bucket is zeroed here."""
+    bucket.reattach()
+    if not accumulate:
+        bucket.zero()
     preds = model(imgs)
     lbox, lobj, lcls, loss = compute_loss(preds, targets, cfg, imgs.device)
     loss.backward()
-    bucket.allreduce_mean(group)
-    optimizer.step()
+    if step:
+        bucket.allreduce_mean(group)
+        optimizer.step()
     return lbox, lobj, lcls, loss

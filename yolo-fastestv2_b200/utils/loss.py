@@ -23,12 +23,19 @@ class _LossFn(torch.autograd.Function):
     def forward(ctx, targets, cfg, *preds):
         losses, dpreds = yfv2_engine.compute_loss(preds, targets, cfg, want_grads=True)
         ctx.save_for_backward(*dpreds)
+        ctx.set_materialize_grads(False)
         return losses[0:1], losses[1:2], losses[2:3], losses[3:4]
 
     @staticmethod
     def backward(ctx, g_box, g_obj, g_cls, g_total):
         # The kernel differentiates the SUM (what train.py:110 back-propagates); the three parts are only logged.
+        # Back-propagating a part would silently give zeros, so it is refused instead.
+        if g_box is not None or g_obj is not None or g_cls is not None:
+            raise RuntimeError("yfv2 compute_loss: only the total loss (4th return value) is differentiable; "
+                               "lbox / lobj / lcls are returned for logging (reference train.py:110 back-propagates the sum)")
         dpreds = ctx.saved_tensors
+        if g_total is None:
+            return (None, None) + tuple(None for _ in dpreds)
         return (None, None) + tuple(d * g_total for d in dpreds)
 
 

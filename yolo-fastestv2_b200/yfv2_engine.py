@@ -30,6 +30,7 @@ PROTOTYPES = {
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "yfv2_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "yfv2_plan_workspace_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "yfv2_plan_invalidate_workspace": (ctypes.c_int, [ctypes.c_void_p]),
     "yfv2_plan_packed_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
     "yfv2_plan_forward_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
     "yfv2_pack_weights": (ctypes.c_int, [ctypes.c_void_p, _c_void_pp, _c_void_pp, ctypes.c_void_p, ctypes.c_void_p]),
@@ -49,6 +50,8 @@ PROTOTYPES = {
                                        ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_void_p,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_batch_statistics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_detect_u8_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -259,7 +262,10 @@ def decode(preds, cfg):
 def _filter_tensor(classes, device):
     if classes is None:
         return None, 0
-    t = torch.as_tensor(list(classes), dtype=torch.int32, device=device)
+    classes = list(classes)
+    if not classes:
+        classes = [-1]      # the reference keeps rows whose class is IN the list (utils/utils.py:266-268): an empty list keeps nothing
+    t = torch.as_tensor(classes, dtype=torch.int32, device=device)
     return t, t.numel()
 
 
@@ -299,6 +305,20 @@ def decode_nms(preds, cfg, conf_thres=0.3, iou_thres=0.45, classes=None, max_det
                                      ctypes.c_float(MAX_WH), ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(counts.data_ptr()),
                                      ctypes.c_void_p(idx.data_ptr()) if want_idx else None, None, _stream(dev)), "decode_nms")
     return out, counts, idx
+
+
+def batch_statistics(out, counts, targets, iou_threshold):
+    """True-positive flags [N,max_det] (float 0/1) of NMS output rows against pixel-xyxy targets [nt,6] (device)."""
+    _require_cuda(out, "out")
+    N, max_det, _ = out.shape
+    targets = targets.detach().to(out.device).float().contiguous().reshape(-1, 6)
+    tp = torch.empty((N, max_det), dtype=torch.float32, device=out.device)
+    with torch.cuda.device(out.device):
+        _check(lib().yfv2_batch_statistics(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(counts.data_ptr()), N, max_det,
+                                           ctypes.c_void_p(targets.data_ptr()) if targets.numel() else None, targets.shape[0],
+                                           ctypes.c_float(iou_threshold), ctypes.c_void_p(tp.data_ptr()), _stream(out.device)),
+               "batch_statistics")
+    return tp
 
 
 def debug_pw_tc(x, w):
