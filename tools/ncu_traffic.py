@@ -16,6 +16,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STEPS = 3
+# the forward / post-processing kernels only (weight packing and torch fills also launch during the run)
+KERNELS = "regex:^(stem|s1c_|s2c_|pw3_|tail_|tc_|decode_nms|nms_|decode_)"
 
 
 def group_labels():
@@ -60,7 +62,7 @@ def capture(path):
     labels = group_labels()
     per_step = len(labels) + 1                       # + fused decode/NMS
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
-           "-s", str((STEPS - 1) * per_step), "-c", str(per_step), "--csv", "--log-file", path,
+           "-k", KERNELS, "-s", str((STEPS - 1) * per_step), "-c", str(per_step), "--csv", "--log-file", path,
            sys.executable, os.path.join(ROOT, "tools", "prof_fwd.py"), str(STEPS)]
     print(" ".join(cmd), flush=True)
     sys.exit(subprocess.call(cmd))

@@ -14,6 +14,8 @@
 //   * the A operand goes to the tensor core in chunks of KC channels (16 or the whole K) instead of 8;
 //   * every per-channel plane offset is a kernel-parameter constant (no table lookups / multiplies in the loops),
 //     weights reach shared memory by cp.async.bulk (UBLKCP), invalid lanes are clamped instead of predicated.
+#include <cstdlib>
+
 #include "eng3.cuh"
 
 namespace yfv2 {
@@ -39,12 +41,13 @@ __device__ __forceinline__ void acquire_buf(BGrp& g) {
     if (use > 0) mbar_wait(&g.pipe->empty[buf], (use - 1) & 1u);
     fence_after_sync();
 }
-// KC channel values of one of this thread's two pixels -> tf32 hi / lo columns of the current A buffer.
-template <int KC, int NB>
-__device__ __forceinline__ void store_a(const BGrp& g, int tile, const float* a) {
-    const uint32_t col = g.tlane + (g.chunk % NB) * (4 * KC) + tile * (2 * KC);
+// KCS (= KC / siblings) channel values of one of this thread's two pixels -> tf32 hi / lo columns [koff, koff + KCS) of the
+// current A buffer.
+template <int KC, int NB, int KCS = KC>
+__device__ __forceinline__ void store_a(const BGrp& g, int tile, const float* a, int koff = 0) {
+    const uint32_t col = g.tlane + (g.chunk % NB) * (4 * KC) + tile * (2 * KC) + koff;
 #pragma unroll
-    for (int j = 0; j < KC; j += 8) {
+    for (int j = 0; j < KCS; j += 8) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -56,7 +59,7 @@ __device__ __forceinline__ void store_a(const BGrp& g, int tile, const float* a)
     }
 }
 // Chunk c (of KP / KC) of both tiles is in TMEM: the last of the group's four warps to get here issues the MMAs.
-template <int KP, int NP, int KC, int NB>
+template <int KP, int NP, int KC, int NB, int SIB = 1>
 __device__ __forceinline__ void hand_off(BGrp& g, int c, uint32_t b_hi, uint32_t b_lo) {
     wait_st();
     fence_before_sync();
@@ -64,7 +67,7 @@ __device__ __forceinline__ void hand_off(BGrp& g, int c, uint32_t b_hi, uint32_t
     if ((threadIdx.x & 31) == 0) {
         const uint32_t buf = g.chunk % NB;
         const uint32_t old = atom_inc_acq_rel(&g.pipe->arrivals[buf]);
-        if ((old & 3u) == 3u) {
+        if ((old & (4u * SIB - 1u)) == 4u * SIB - 1u) {
             fence_after_sync();
             constexpr uint32_t idesc = make_idesc_tf32(128, NP);
             constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
@@ -128,13 +131,17 @@ struct S1Smem {
 // consecutive words in consecutive lanes (no bank conflicts); the left/right zero padding is a per-thread multiplier.
 __host__ __device__ constexpr int t_half_floats(int TR, int W) { return ((TR + 3) / 2) * W + 2; }     // one of E / O, 1 pad float each side
 
-template <int K, int NP, int G, int KC, int NB>
-__global__ void __launch_bounds__(G * 128, 1)
+// SIB sibling warps per TMEM lane quarter (1 or 2): warps w and w + 4 of a group share the same 32 pixel pairs; each computes KC / SIB
+// of a chunk's channels and drains one of the pair's two accumulator tiles.  K = 48 ran 8 warps per SM at 232 registers (ncu:
+// issue slots 37 % busy, 12 % warps active); TMEM allows no third group, siblings double the warps on the same columns.
+template <int K, int NP, int G, int KC, int NB, int SIB = 1>
+__global__ void __launch_bounds__(G * 128 * SIB, 1)
 s1c_kernel(const __grid_constant__ S1cArgs p) {
     pdl_trigger();
     constexpr int KP = K;
     constexpr int COLS = NB * 4 * KC + 2 * NP;
-    static_assert(G * COLS <= 512 && K % KC == 0 && KC % 8 == 0 && NP % 16 == 0 && K <= kMaxK, "shape");
+    constexpr int KCS = KC / SIB, NT = G * 128 * SIB;
+    static_assert(G * COLS <= 512 && K % KC == 0 && KCS % 8 == 0 && NP % 16 == 0 && K <= kMaxK && (SIB == 1 || SIB == 2), "shape");
     using L = S1Smem<K, NP>;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) BPipe pipes[G];
@@ -171,12 +178,14 @@ s1c_kernel(const __grid_constant__ S1cArgs p) {
         if (total_sets > 1 && p.wbufs > 1) load_wset(1);
     }
     if (warp == 0) tmem_alloc(&tmem_slot, 512);
-    for (int i = threadIdx.x; i < K * TP; i += G * 128) T[i] = 0.f;      // halo rows and pads stay zero
+    for (int i = threadIdx.x; i < K * TP; i += NT) T[i] = 0.f;      // halo rows and pads stay zero
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     BGrp g;
-    const int grp = threadIdx.x >> 7;
+    const int grp = threadIdx.x / (128 * SIB);
+    const int sub = SIB == 1 ? 0 : (warp >> 2) & 1;         // sibling index; the lane quarter is warp & 3 either way
+    const int koff = sub * KCS;
     g.tcol = tmem_slot + grp * COLS;
     g.tlane = g.tcol + ((uint32_t)(32 * (warp & 3)) << 16);
     g.pipe = &pipes[grp];
@@ -194,11 +203,11 @@ s1c_kernel(const __grid_constant__ S1cArgs p) {
         const int tr_lo = r0 == 0 ? 1 : 0, tr_hi = (r0 + rows == H) ? rows : rows + 1;
         if (p.bandsPerImg > 1) {
             // band items: halo rows outside the image must read as zero (a previous item may have left data there)
-            if (r0 == 0) for (int i = threadIdx.x; i < K * W; i += G * 128) { const int k = i / W; T[k * TP + 1 + (i - k * W)] = 0.f; }
+            if (r0 == 0) for (int i = threadIdx.x; i < K * W; i += NT) { const int k = i / W; T[k * TP + 1 + (i - k * W)] = 0.f; }
             if (r0 + rows == H) {
                 const int tr = rows + 1;
                 const int o = (tr & 1) * TH + 1 + (tr >> 1) * W;
-                for (int i = threadIdx.x; i < K * W; i += G * 128) { const int k = i / W; T[k * TP + o + (i - k * W)] = 0.f; }
+                for (int i = threadIdx.x; i < K * W; i += NT) { const int k = i / W; T[k * TP + o + (i - k * W)] = 0.f; }
             }
             __syncthreads();
         }
@@ -230,28 +239,29 @@ s1c_kernel(const __grid_constant__ S1cArgs p) {
                 const int gr0 = r0 - 1 + (tr0 >= tr_lo ? tr0 : tr1), gr1 = r0 - 1 + (tr1 <= tr_hi ? tr1 : tr0);
                 const float* ip0 = img + gr0 * p.P.Ws + x;
                 const float* ip1 = img + gr1 * p.P.Ws + x;
-                float v[2][2 * KC];                                 // [buffer][tile * KC + j]: next chunk's loads fly during this chunk's hand-off
+                float v[2][2 * KCS];                                // [buffer][tile * KCS + j]: next chunk's loads fly during this chunk's hand-off
 #pragma unroll
-                for (int j = 0; j < KC; ++j) { v[0][j] = __ldcg(ip0 + ioff[j]); v[0][KC + j] = __ldcg(ip1 + ioff[j]); }
+                for (int j = 0; j < KCS; ++j) { v[0][j] = __ldcg(ip0 + ioff[koff + j]); v[0][KCS + j] = __ldcg(ip1 + ioff[koff + j]); }
 #pragma unroll
                 for (int c = 0; c < K / KC; ++c) {
                     if (c + 1 < K / KC) {
 #pragma unroll
-                        for (int j = 0; j < KC; ++j) {
-                            v[(c + 1) & 1][j] = __ldcg(ip0 + ioff[(c + 1) * KC + j]);
-                            v[(c + 1) & 1][KC + j] = __ldcg(ip1 + ioff[(c + 1) * KC + j]);
+                        for (int j = 0; j < KCS; ++j) {
+                            v[(c + 1) & 1][j] = __ldcg(ip0 + ioff[(c + 1) * KC + koff + j]);
+                            v[(c + 1) & 1][KCS + j] = __ldcg(ip1 + ioff[(c + 1) * KC + koff + j]);
                         }
                     }
                     acquire_buf<KC, NB>(g);
-                    store_a<KC, NB>(g, 0, v[c & 1]);
-                    store_a<KC, NB>(g, 1, v[c & 1] + KC);
-                    hand_off<KP, NP, KC, NB>(g, c, b1_hi, b1_lo);
+                    store_a<KC, NB, KCS>(g, 0, v[c & 1], koff);
+                    store_a<KC, NB, KCS>(g, 1, v[c & 1] + KCS, koff);
+                    hand_off<KP, NP, KC, NB, SIB>(g, c, b1_hi, b1_lo);
                 }
                 wait_d<KC, NB>(g);
                 float* te = T + 1 + i * W + x;                      // E row i      (tr1)
                 float* to = T + TH + 1 + (i - 1) * W + x;           // O row i - 1  (tr0)
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
+                    if (SIB == 2 && t != sub) continue;             // sibling s drains tile s
                     float d[NP];
                     load_d<NP, KC, NB>(g, t, d);
                     if (t == 0 ? v0 : v1) {
@@ -283,12 +293,12 @@ s1c_kernel(const __grid_constant__ S1cArgs p) {
                 const float* to = te + TH;
 #pragma unroll 1
                 for (int c = 0; c < K / KC; ++c) {
-                    float a0[KC], a1[KC];
-                    const float* e = te + c * KC * TP;
-                    const float* o = to + c * KC * TP;
-                    const float* wk = sDW + c * KC * 12;
+                    float a0[KCS], a1[KCS];
+                    const float* e = te + (c * KC + koff) * TP;
+                    const float* o = to + (c * KC + koff) * TP;
+                    const float* wk = sDW + (c * KC + koff) * 12;
 #pragma unroll
-                    for (int jj = 0; jj < KC; ++jj) {
+                    for (int jj = 0; jj < KCS; ++jj) {
                         const float4 wa = *reinterpret_cast<const float4*>(wk);
                         const float4 wb4 = *reinterpret_cast<const float4*>(wk + 4);
                         const float4 wc = *reinterpret_cast<const float4*>(wk + 8);
@@ -310,14 +320,15 @@ s1c_kernel(const __grid_constant__ S1cArgs p) {
                         e += TP; o += TP; wk += 12;
                     }
                     acquire_buf<KC, NB>(g);
-                    store_a<KC, NB>(g, 0, a0);
-                    store_a<KC, NB>(g, 1, a1);
-                    hand_off<KP, NP, KC, NB>(g, c, b2_hi, b2_lo);
+                    store_a<KC, NB, KCS>(g, 0, a0, koff);
+                    store_a<KC, NB, KCS>(g, 1, a1, koff);
+                    hand_off<KP, NP, KC, NB, SIB>(g, c, b2_hi, b2_lo);
                 }
                 wait_d<KC, NB>(g);
                 float* op = img + (r0 + 2 * j) * p.P.Ws + ox;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
+                    if (SIB == 2 && t != sub) continue;
                     float d[NP];
                     load_d<NP, KC, NB>(g, t, d);
                     if (t == 0 ? v0 : v1) {
@@ -749,15 +760,17 @@ int blk_launch_s1(int K, const Planes& P, int nblk, const ChanTab* tin, const Ch
         }
     }
     const int items = N * geo.bands;
-    auto run = [&](auto kern, int G) -> int {
+    auto run = [&](auto kern, int threads) -> int {
         TRYB(blk_smem_attr(kern, geo.bytes));
-        YFV2_CUDA(launch_k(kern, min(items, sm_count()), G * 128, geo.bytes, s, pdl_take(), a));
+        YFV2_CUDA(launch_k(kern, min(items, sm_count()), threads, geo.bytes, s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
     *done = nblk;
-    if (K == 24) return run(s1c_kernel<24, 32, 4, 8, 2>, 4);
-    return run(s1c_kernel<48, 48, 2, 16, 2>, 2);
+    static const bool no_sib = getenv("YFV2_S1_NOSIB") != nullptr;          // one warp per lane quarter, kept for A/B runs
+    if (K == 24) return run(s1c_kernel<24, 32, 4, 8, 2>, 4 * 128);
+    if (no_sib) return run(s1c_kernel<48, 48, 2, 16, 2>, 2 * 128);
+    return run(s1c_kernel<48, 48, 2, 16, 2, 2>, 2 * 256);
 }
 
 // Stride-2 block of branch width K (24 or 48): in (K planes at 2H x 2W) -> out (2K planes at H x W).

@@ -781,6 +781,233 @@ tc_head2_kernel(const __grid_constant__ HeadArgs p) {
 }
 
 // ===================================================================================================
+// tc_head2w_kernel: tc_head2_kernel with SIBLING WARPS.  ncu on tc_head2_kernel (profiles/r2_kernels_ncu.txt): 9 warps per SM,
+// issue slots 29 % busy, stalls spread over long/short scoreboard and MIO throttle: two warps per scheduler cannot hide the
+// LDS -> FFMA chains of the 5x5 stencil, and TMEM (2 groups x 256 columns) rules out more warpgroups.  A warp may only touch
+// the TMEM lanes 32 (warp % 4) .. +31, but nothing says ONE warp per lane quarter: here warps w and w + 4 of a group share the
+// same 32 pixel pairs and each computes half of a chunk's channels (4 of 8: columns [4 sub, 4 sub + 4) of the hi / lo blocks),
+// the chunk's MMAs are issued by the last of the group's EIGHT warps, and in the epilogue sibling 0 drains tile 0 (the pair's
+// left pixel) while sibling 1 drains tile 1.  17 warps per SM on the same TMEM and shared-memory footprint.
+// ===================================================================================================
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+template <bool RELU>
+__device__ __forceinline__ void dw5_pair4(const float* __restrict__ xk, int RS, int WS, const float* __restrict__ wk, bool valid0, bool valid1,
+                                          float (&a0)[4], float (&a1)[4]) {
+    if (!valid0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float w[28];
+#pragma unroll
+        for (int t = 0; t < 7; ++t) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + 4 * t);
+            w[4 * t] = w4.x; w[4 * t + 1] = w4.y; w[4 * t + 2] = w4.z; w[4 * t + 3] = w4.w;
+        }
+        float p0[5], p1[5];
+        const float* row = xk;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+            const float2 v01 = *reinterpret_cast<const float2*>(row);
+            const float2 v23 = *reinterpret_cast<const float2*>(row + 2);
+            const float2 v45 = *reinterpret_cast<const float2*>(row + 4);
+            const float v[6] = {v01.x, v01.y, v23.x, v23.y, v45.x, v45.y};
+            p0[dy] = w[dy * 5] * v[0];
+            p1[dy] = w[dy * 5] * v[1];
+#pragma unroll
+            for (int dx = 1; dx < 5; ++dx) {
+                p0[dy] = fmaf(w[dy * 5 + dx], v[dx], p0[dy]);
+                p1[dy] = fmaf(w[dy * 5 + dx], v[dx + 1], p1[dy]);
+            }
+            row += WS;
+        }
+        float d0 = ((p0[0] + p0[1]) + (p0[2] + p0[3])) + p0[4];      // same association as dw8p
+        float d1 = ((p1[0] + p1[1]) + (p1[2] + p1[3])) + p1[4];
+        d0 = fmaf(d0, w[25], w[26]);
+        d1 = fmaf(d1, w[25], w[26]);
+        if (RELU) { d0 = fmaxf(d0, 0.f); d1 = fmaxf(d1, 0.f); }
+        a0[j] = d0;
+        a1[j] = valid1 ? d1 : 0.f;
+        xk += RS;
+        wk += 28;
+    }
+}
+// four channels (sibling `sub`) of chunk c of both tiles -> TMEM; the last of the group's eight warps issues the chunk's MMAs
+template <int KP, int NP>
+__device__ __forceinline__ void put_chunk2w(Grp& g, int sub, const float (&a0)[4], const float (&a1)[4], int c, uint32_t b_hi, uint32_t b_lo) {
+    const uint32_t buf = g.chunk & 1u, use = g.chunk >> 1;
+    if (use > 0) mbar_wait(&g.pipe->empty[buf], (use - 1) & 1u);
+    fence_after_sync();
+    {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hi[i] = __float_as_uint(a0[i]) & 0xFFFFE000u; lo[i] = __float_as_uint(a0[i] - __uint_as_float(hi[i])); }
+        tmem_st4(g.tlane + buf * 32 + 4 * sub, hi);
+        tmem_st4(g.tlane + buf * 32 + 8 + 4 * sub, lo);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hi[i] = __float_as_uint(a1[i]) & 0xFFFFE000u; lo[i] = __float_as_uint(a1[i] - __uint_as_float(hi[i])); }
+        tmem_st4(g.tlane + buf * 32 + 16 + 4 * sub, hi);
+        tmem_st4(g.tlane + buf * 32 + 24 + 4 * sub, lo);
+    }
+    wait_st();
+    fence_before_sync();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t old = atom_add_acq_rel(&g.pipe->arrivals[buf], 1u);
+        if ((old & 7u) == 7u) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_tf32(128, NP);
+            constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
+            const uint64_t bh = make_b_desc(b_hi + c * 256, LBO, SBO);
+            const uint64_t bl = make_b_desc(b_lo + c * 256, LBO, SBO);
+#pragma unroll
+            for (int tile = 0; tile < 2; ++tile) {
+                const uint32_t a_hi = g.tcol + buf * 32 + tile * 16, a_lo = a_hi + 8, d = g.tcol + kA2Cols + tile * NP;
+                mma_tf32_ts(d, a_lo, bh, idesc, c > 0 ? 1u : 0u);
+                mma_tf32_ts(d, a_hi, bl, idesc, 1u);
+                mma_tf32_ts(d, a_hi, bh, idesc, 1u);
+            }
+            mma_commit(&g.pipe->empty[buf]);
+            if (c == KP / 8 - 1) mma_commit(&g.pipe->dfull);
+        }
+    }
+    __syncwarp();
+    ++g.chunk;
+}
+
+template <int K, int NP, bool DENSE>
+__global__ void __launch_bounds__(2 * 256 + 32, 1)
+tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
+    pdl_trigger();
+    constexpr int G = 2, GT = 256, NCH = K / 8, NB = kHeadBufs, DWR = 28, COLS = 256, TOT = 512;
+    static_assert(K % 8 == 0 && NP % 16 == 0 && kA2Cols + 2 * NP <= COLS, "shape");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) Pipe pipes[G];
+    __shared__ __align__(8) uint64_t fullb[NB], freeb[NB];
+    __shared__ uint32_t tmem_slot;
+    constexpr int WFL = 2 * NP * K + 2 * NP;
+    float* sB = smem;
+    float* sDW = sB + WFL;
+    float* X = sDW + K * DWR;
+    const int H = p.in[0].H, W = p.in[0].W, WS = p.in[0].Ws;
+    const int PS = (H + 4) * WS;
+    const int CS = PS * p.imgs;
+    const int BUF = 8 * CS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullb[i], 1); mbar_init(&freeb[i], G * 8); }
+        for (int i = 0; i < G; ++i) {
+            for (int b = 0; b < kMaxABufs; ++b) { mbar_init(&pipes[i].empty[b], 1); pipes[i].arrivals[b] = 0; }
+            mbar_init(&pipes[i].dfull, 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, TOT);
+    const int ngroups = (p.N + p.imgs - 1) / p.imgs;
+    const int items = 2 * ngroups;
+    const int first_branch = (int)blockIdx.x / ngroups;
+    if (threadIdx.x < G * GT) {
+        copy_f4(sB, p.wpw[first_branch], WFL, G * GT);
+        copy_f4(sDW, p.wdw[first_branch], K * DWR, G * GT);
+        publish_smem();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    pdl_wait();
+    uint32_t it = 0;
+    if (warp == G * 8) {
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const uint32_t buf = it % NB, use = it / NB;
+                if (use > 0) mbar_wait(&freeb[buf], (use - 1) & 1u);
+                publish_smem();
+                if (lane == 0) mbar_expect_tx(&fullb[buf], (uint32_t)(8 * nimg * PS * sizeof(float)));
+                __syncwarp();
+                for (int j = lane; j < 8 * nimg; j += 32) {
+                    const int ch = j & 7, i = j >> 3;
+                    bulk_g2s(X + (size_t)buf * BUF + ch * CS + i * PS, plane_ptr(p.in[br], n0 + i, c * 8 + ch),
+                             (uint32_t)(PS * sizeof(float)), &fullb[buf]);
+                }
+            }
+        }
+    } else {
+        const int grp = threadIdx.x >> 8, sub = (warp >> 2) & 1;
+        Grp g;
+        g.tcol = tmem_slot + grp * COLS;
+        g.tlane = g.tcol + ((uint32_t)(32 * (warp & 3)) << 16);
+        g.pipe = &pipes[grp];
+        g.chunk = 0; g.dparity = 0;
+        g.gtid = threadIdx.x & 127;
+        const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * K);
+        const float* scale = sB + 2 * NP * K;
+        const float* shift = scale + NP;
+        const int HW = H * W;
+        const int Wp = (W + 1) >> 1, PPI = H * Wp;          // pixel pairs per row / per image
+        int loaded_branch = first_branch;
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            if (br != loaded_branch) {
+                group_bar(1, G * GT);
+                copy_f4(sB, p.wpw[br], WFL, G * GT);
+                copy_f4(sDW, p.wdw[br], K * DWR, G * GT);
+                publish_smem();
+                group_bar(1, G * GT);
+                loaded_branch = br;
+            }
+            const int q = grp * 128 + g.gtid;               // pair index inside the item
+            const bool valid0 = q < PPI * nimg;
+            const int im = valid0 ? q / PPI : 0;
+            const int qi = valid0 ? q - im * PPI : 0;
+            const int oy = qi / Wp, ox = 2 * (qi - oy * Wp);
+            const bool valid1 = valid0 && ox + 1 < W;
+            const int woff = im * PS + oy * WS + ox;        // even: the three LDS.64 of a window row are aligned
+            // sibling `sub` drains tile `sub` (the pair's pixel ox + sub)
+            RowSink<false, DENSE, true> sink;
+            sink.scale = scale; sink.shift = shift; sink.valid = sub ? valid1 : valid0;
+            if (!DENSE) {
+                sink.obase = p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox + sub;
+                sink.tout = nullptr; sink.sCo = (unsigned)p.out[br].sC; sink.nout = p.nout;
+            } else {
+                sink.dA = p.dstA[br]; sink.dB = p.dstB[br]; sink.split = p.split[br]; sink.M = p.M[br];
+                sink.n = n0 + im; sink.HW = HW; sink.opix = oy * W + ox + sub;
+            }
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c, ++it) {
+                const uint32_t buf = it % NB;
+                mbar_wait(&fullb[buf], (it / NB) & 1u);
+                float a0[4], a1[4];
+                dw5_pair4<true>(X + (size_t)buf * BUF + 4 * sub * CS + woff, CS, WS, sDW + (c * 8 + 4 * sub) * DWR, valid0, valid1, a0, a1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&freeb[buf]);
+                put_chunk2w<K, NP>(g, sub, a0, a1, c, b_hi, b_lo);
+            }
+            mbar_wait(&g.pipe->dfull, g.dparity);
+            g.dparity ^= 1u;
+            fence_after_sync();
+            const int ncols = DENSE ? p.M[br] : p.nout;
+#pragma unroll 1
+            for (int n0c = 0; n0c < ncols; n0c += 16) {
+                float d[16];
+                tmem_ld16(g.tlane + kA2Cols + sub * NP + n0c, d);
+                wait_ld();
+                sink(n0c, d);
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_slot, TOT);
+}
+
+// ===================================================================================================
 // tc_s1_kernel: fused stride-1 ShuffleV2 block (reference shufflenetv2.py:19-32,48-51).
 // ===================================================================================================
 struct S1Args {
@@ -1348,14 +1575,19 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         const size_t bytes = (wfl + kHeadBufs * 8 * PS * a.imgs + 4) * sizeof(float);
         if (bytes <= kSmemCap - 1024) {
             const int ngroups = (N + a.imgs - 1) / a.imgs;
-            auto run = [&](auto kern) -> int {
+            static const bool old_heads = getenv("YFV2_HEADS_OLD") != nullptr;     // round-1 kernel (one warp per lane quarter), kept for A/B runs
+            auto run = [&](auto kern, int threads) -> int {
                 TRYL(set_smem_attr(kern, bytes));
-                YFV2_CUDA(launch_k(kern, min(2 * ngroups, sm_count()), 2 * 128 + 32, bytes, s, pdl_take(), a));
+                YFV2_CUDA(launch_k(kern, min(2 * ngroups, sm_count()), threads, bytes, s, pdl_take(), a));
                 YFV2_LAUNCH_CHECK();
                 return YFV2_OK;
             };
-            if (half == 0) return run(tc_head2_kernel<72, 80, false>);
-            return run(tc_head2_kernel<72, 96, true>);
+            if (old_heads) {
+                if (half == 0) return run(tc_head2_kernel<72, 80, false>, 2 * 128 + 32);
+                return run(tc_head2_kernel<72, 96, true>, 2 * 128 + 32);
+            }
+            if (half == 0) return run(tc_head2w_kernel<72, 80, false>, 2 * 256 + 32);
+            return run(tc_head2w_kernel<72, 96, true>, 2 * 256 + 32);
         }
     }
     if (H * W <= 512 && !force_band) {

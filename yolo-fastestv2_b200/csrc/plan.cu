@@ -519,6 +519,8 @@ extern "C" int yfv2_pack_weights(yfv2_plan* p, const float* const* params, const
 }
 
 namespace yfv2 {
+bool stem2_supported(const StemArgs& a);
+int launch_stem2(const StemArgs& a, cudaStream_t s);
 int tc_launch_stem(const void* x, int is_u8, const Planes& out, const float* wpack, int N, int H, int W, cudaStream_t s);
 int tc_launch_s1(int K, const Planes& P, const ChanTab& tin, const ChanTab& tout, const float* w1, const float* wdw, const float* w2,
                  int N, cudaStream_t s);
@@ -572,9 +574,13 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
         switch (st.kind) {
         case 0: {
             static const bool stem_tc = getenv("YFV2_STEM_TC") != nullptr;
-            if (!stem_tc) {   // default: register-tiled FFMA direct convolution (k_stem.cu explains why)
+            static const bool stem_ffma = getenv("YFV2_STEM_FFMA") != nullptr;   // round-1 FFMA2 stem, kept for A/B runs
+            if (!stem_tc) {
                 StemArgs a{x, is_u8, p->N, p->H, p->W, pool_planes(p, ws, 0), pk + p->pk_stem};
-                TRY(launch_stem(a, s));
+                // default: the tensor-core strip walk (k_stem2.cu); the register-tiled FFMA2 direct convolution (k_stem.cu)
+                // takes over for inputs whose base address is not 16-byte (uint8: 4-byte) aligned
+                if (!stem_ffma && stem2_supported(a)) { TRY(launch_stem2(a, s)); }
+                else { TRY(launch_stem(a, s)); }
             } else {
                 TRY(tc_launch_stem(x, is_u8, pool_planes(p, ws, 0), pk + p->tk_stem, p->N, p->H, p->W, s));
             }
