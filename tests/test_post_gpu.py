@@ -116,3 +116,20 @@ def test_nms_microbench_properties_at_scale():
     again[0, torch.arange(n), 5 + kept[:, 5].long()] = kept[:, 4]
     o2, c2, i2 = eng.nms(again, 0.001, 0.4)
     assert int(c2[0]) == n and torch.equal(i2[0, :n].long().cpu(), torch.arange(n))
+
+
+def test_nms_boxes_wider_than_the_class_offset():
+    """Boxes outside (-max_wh/2, max_wh/2) can overlap across classes after the class offset of utils/utils.py:283; the kernel
+    then must not skip pairs on their class ids (the by-class shortcut is only taken for images whose boxes all fit).  One image
+    of each kind in the same batch, bit-exact against the oracle."""
+    d = synth.make_dets(91, 2, 400)
+    d[1, :, 2] = d[1, :, 2] * 40.0 + 3000.0            # widths of several thousand pixels: neighbouring classes intersect
+    d[1, :, 0] = d[1, :, 0] * 3.0
+    for ct, it in THR[:3]:
+        out, counts, idx = eng.nms(d.cuda(), ct, it)
+        rows, oidx = opost.nms(d, ct, it, return_indices=True)
+        for i in range(2):
+            c = int(counts[i])
+            assert c == rows[i].shape[0], (ct, it, i)
+            assert np.array_equal(out[i, :c].cpu().numpy(), rows[i].numpy()), (ct, it, i)
+            assert np.array_equal(idx[i, :c].cpu().numpy(), oidx[i]), (ct, it, i)

@@ -220,13 +220,16 @@ struct NmsSmem {
     float4* chbox;              // [64]
     float* charea;              // [64]
     unsigned int* cmask;        // [64][2]
-    unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits
+    unsigned short* kcls;       // [max_det] class of kept
+    unsigned short* chcls;      // [64]
+    unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits, [5]=some box outside (-max_wh/2, max_wh/2)
 };
 
 __host__ __device__ inline size_t nms_smem_bytes(int M, int MCp, int max_det) {
     size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (((size_t)M * 2 + 15) & ~(size_t)15);
     b += (size_t)max_det * 16 + (((size_t)max_det * 4 + 15) & ~(size_t)15);
     b += kNmsChunk * 16 + kNmsChunk * 4 + kNmsChunk * 8 + 32;
+    b += (((size_t)max_det * 2 + 15) & ~(size_t)15) + kNmsChunk * 2;
     return b;
 }
 
@@ -240,7 +243,9 @@ __device__ __forceinline__ NmsSmem carve(unsigned char* base, int M, int MCp, in
     s.chbox = reinterpret_cast<float4*>(base); base += kNmsChunk * 16;
     s.charea = reinterpret_cast<float*>(base); base += kNmsChunk * 4;
     s.cmask = reinterpret_cast<unsigned int*>(base); base += kNmsChunk * 8;
-    s.misc = reinterpret_cast<unsigned int*>(base);
+    s.misc = reinterpret_cast<unsigned int*>(base); base += 32;
+    s.kcls = reinterpret_cast<unsigned short*>(base); base += (((size_t)max_det * 2 + 15) & ~(size_t)15);
+    s.chcls = reinterpret_cast<unsigned short*>(base);
     return s;
 }
 
@@ -260,10 +265,16 @@ __device__ __forceinline__ bool class_ok(const NmsParams& p, int cls) {
 }
 
 // xywh -> xyxy (utils/utils.py:67-74) and store candidate `slot`; called by the lane that owns the candidate.
+// Also records whether every box of the image lies inside (-max_wh/2, max_wh/2): then the class offsets of utils/utils.py:283 put
+// the classes on disjoint intervals, boxes of different classes can never intersect (their fp32 intersection width is exactly 0,
+// rounding is monotone) and the suppression phases may skip such pairs by comparing class ids — bit-identical to testing them.
 __device__ __forceinline__ void write_candidate(const NmsSmem& s, unsigned int slot, float cx, float cy, float w, float h, float conf,
-                                                int cls, int row) {
+                                                int cls, int row, float max_wh) {
     const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-    s.cbox[slot] = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    const float4 bb = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+    const float lim = 0.5f * max_wh;
+    if (!(fabsf(bb.x) < lim && fabsf(bb.y) < lim && fabsf(bb.z) < lim && fabsf(bb.w) < lim)) s.misc[5] = 1u;    // (NaN lands here too)
+    s.cbox[slot] = bb;
     s.ccls[slot] = (unsigned short)cls;
     s.keys[slot] = ((unsigned long long)f2sortable(conf) << 32) |
                    ((unsigned long long)(0xFFFFu - (unsigned)row) << 16) | (unsigned long long)slot;
@@ -370,6 +381,9 @@ __device__ void bitonic_sort_desc_reg(unsigned long long* keys) {
 __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
     __syncthreads();
     const int cnt = (int)s.misc[0];
+    // classes on disjoint intervals (see write_candidate) and a threshold whose rounding boundary is positive: pairs of different
+    // classes have IoU exactly 0 and are skipped on their class ids
+    const bool by_class = s.misc[5] == 0u && p.iou_mid > 0.0 && p.max_wh > 0.f;
     int n2 = 64;
     while (n2 < cnt) n2 <<= 1;
     for (int i = cnt + threadIdx.x; i < n2; i += NT) s.keys[i] = 0ull;
@@ -395,13 +409,23 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
                 const float4 ob = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
                 s.chbox[t] = ob;
                 s.charea[t] = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
+                s.chcls[t] = s.ccls[slot];
             }
         }
         if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }
         __syncthreads();
         {   // (a) chunk candidates against everything kept so far
             const int j = t & (kNmsChunk - 1), q = t / kNmsChunk;
-            if (j < cn) {
+            if (j < cn && by_class) {
+                const float4 bj = s.chbox[j];
+                const float aj = s.charea[j];
+                const unsigned short cj = s.chcls[j];
+                bool dead = false;
+                constexpr int STEP = NT / kNmsChunk;
+                for (int i = q; i < nk && !dead; i += STEP)
+                    if (s.kcls[i] == cj) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
+                if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
+            } else if (j < cn) {
                 const float4 bj = s.chbox[j];
                 const float aj = s.charea[j];
                 // four kept boxes per trip: the loads and IoU tests are independent, only the exit test is shared
@@ -424,11 +448,12 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             if (i < cn) {
                 const float4 bi = s.chbox[i];
                 const float ai = s.charea[i];
+                const unsigned short ci = s.chcls[i];
                 unsigned int bits = 0u;
 #pragma unroll 4
                 for (int e = 0; e < 16; ++e) {
                     const int j = jq * 16 + e;
-                    if (j > i && j < cn && iou_gt(bi, ai, s.chbox[j], s.charea[j], p)) bits |= 1u << e;
+                    if (j > i && j < cn && (!by_class || s.chcls[j] == ci) && iou_gt(bi, ai, s.chbox[j], s.charea[j], p)) bits |= 1u << e;
                 }
                 if (bits) atomicOr(&s.cmask[2 * i + (jq >> 1)], bits << ((jq & 1) * 16));
             }
@@ -455,6 +480,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             const int pos = nk + __popcll(kept & ((1ull << t) - 1ull));
             s.kbox[pos] = s.chbox[t];
             s.karea[pos] = s.charea[t];
+            s.kcls[pos] = s.chcls[t];
             const unsigned long long key = s.keys[c0 + t];
             const unsigned int slot = (unsigned int)(key & 0xFFFFull);
             const float4 b = s.cbox[slot];
@@ -478,7 +504,7 @@ nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
     const int n = blockIdx.x;
-    if (threadIdx.x == 0) s.misc[0] = 0u;
+    if (threadIdx.x == 0) { s.misc[0] = 0u; s.misc[5] = 0u; }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = 5 + C;
@@ -496,7 +522,7 @@ nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
         warp_argmax(best, bi);                                        // :267 first max
         if (lane == 0 && best > p.conf_thres && class_ok(p, bi)) {    // :268, :271-272
             const unsigned int slot = atomicAdd(&s.misc[0], 1u);
-            write_candidate(s, slot, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r);
+            write_candidate(s, slot, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r, p.max_wh);
         }
     }
     sort_and_suppress(s, p, n);
@@ -578,7 +604,7 @@ __device__ __forceinline__ void thread_cell_candidates(const PostGeom& g, const 
             }
         }
         const unsigned int slot = alloc_slots(s, want);
-        if (want) write_candidate(s, slot, bx, by, bw, bh, conf, cls, row0 + cell * A + a);
+        if (want) write_candidate(s, slot, bx, by, bw, bh, conf, cls, row0 + cell * A + a, p.max_wh);
     }
 }
 
@@ -589,7 +615,7 @@ decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
     const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
     float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
     const int n = blockIdx.x;
-    if (threadIdx.x == 0) s.misc[0] = 0u;
+    if (threadIdx.x == 0) { s.misc[0] = 0u; s.misc[5] = 0u; }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A = g.A, C = g.C;
     if (fast) {
@@ -635,7 +661,7 @@ decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
                     if (lane == a && best > p.conf_thres && class_ok(p, bi)) { my_want = true; my_conf = best; my_cls = bi; }
                 }
                 const unsigned int slot = alloc_slots(s, my_want);
-                if (my_want) write_candidate(s, slot, r.bx, r.by, r.bw, r.bh, my_conf, my_cls, row0 + (cell0 + cl) * A + lane);
+                if (my_want) write_candidate(s, slot, r.bx, r.by, r.bw, r.bh, my_conf, my_cls, row0 + (cell0 + cl) * A + lane, p.max_wh);
             }
         }
     }

@@ -567,6 +567,145 @@ tc_head_kernel(const __grid_constant__ HeadArgs p) {
 }
 
 // ===================================================================================================
+// tc_dws2c_kernel: stride-2 depthwise 3x3 + BN -> pointwise + BN + ReLU on SMALL output maps, channel-streamed like the heads
+// (reference shufflenetv2.py:34-44: branch_proj and the tail of branch_main of a stride-2 block; K = 96: stage 4).
+// tc_dwpw_kernel<96,...> staged whole 96-channel bands for two warpgroups: ncu showed 13 % issue slots, 6.9 barrier stalls per issue,
+// 127 us for 71 MB.  Here a work item is (a group of `imgs` whole images, branch): one 128-pixel tile per warpgroup (an 11x11 map
+// is one tile), a producer warp streams the framed input planes four channels at a time through a ring of kDwsBufs slots (one
+// bulk copy per plane) and the stencil of an 8-channel chunk reads two slots.
+// ===================================================================================================
+struct Dws2Args {
+    Planes in[2], out[2];
+    ChanTab tin[2], tout[2];
+    const float* wdw[2];
+    const float* wpw[2];
+    int N, imgs, nbranch, nout;
+};
+constexpr int kDwsBufs = 3;
+
+// depthwise 3x3 + BN of NC consecutive channels of one output pixel (window top-left xk in the first plane, plane stride RS)
+template <int NC>
+__device__ __forceinline__ void dw3n(const float* __restrict__ xk, int RS, int WS, const float* __restrict__ wk, bool valid, float* a) {
+    if (!valid) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) a[j] = 0.f;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const float4 wa = *reinterpret_cast<const float4*>(wk);
+        const float4 wb = *reinterpret_cast<const float4*>(wk + 4);
+        const float4 wc = *reinterpret_cast<const float4*>(wk + 8);
+        const float* r0 = xk; const float* r1 = xk + WS; const float* r2 = xk + 2 * WS;
+        float p0 = wa.x * r0[0]; p0 = fmaf(wa.y, r0[1], p0); p0 = fmaf(wa.z, r0[2], p0);
+        float p1 = wa.w * r1[0]; p1 = fmaf(wb.x, r1[1], p1); p1 = fmaf(wb.y, r1[2], p1);
+        float p2 = wb.z * r2[0]; p2 = fmaf(wb.w, r2[1], p2); p2 = fmaf(wc.x, r2[2], p2);
+        const float d = (p0 + p1) + p2;                     // same association as dw8p<3,...>
+        a[j] = fmaf(d, wc.y, wc.z);
+        xk += RS;
+        wk += 12;
+    }
+}
+
+template <int K, int NP, int G>
+__global__ void __launch_bounds__(G * 128 + 32, 1)
+tc_dws2c_kernel(const __grid_constant__ Dws2Args p) {
+    pdl_trigger();
+    constexpr int NCH = K / 8, NB = kDwsBufs, DWR = 12, COLS = 128, TOT = 512;
+    static_assert(K % 8 == 0 && NP % 16 == 0 && kACols + NP <= COLS && G * COLS <= TOT, "shape");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) Pipe pipes[G + 1];
+    __shared__ __align__(8) uint64_t fullb[NB], freeb[NB];
+    __shared__ uint32_t tmem_slot;
+    constexpr int WFL = 2 * NP * K + 2 * NP;
+    float* sB = smem;
+    float* sDW = sB + WFL;
+    float* X = sDW + K * DWR;
+    const int WS = p.in[0].Ws, pad = p.in[0].pad;
+    const int PS = (p.in[0].H + 2 * pad) * WS;              // one whole framed input plane
+    const int CS = PS * p.imgs;                             // channel stride inside a ring slot
+    const int SLOT = 4 * CS;
+    const int Hout = p.out[0].H, Wout = p.out[0].W, HWo = Hout * Wout;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NB; ++i) { mbar_init(&fullb[i], 1); mbar_init(&freeb[i], G * 4); }
+        fence_mbar_init();
+    }
+    const int ngroups = (p.N + p.imgs - 1) / p.imgs;
+    const int items = p.nbranch * ngroups;                  // branch-major
+    const int first_branch = (int)blockIdx.x / ngroups;
+    if (threadIdx.x < G * 128) {
+        copy_f4(sB, p.wpw[first_branch], WFL, G * 128);
+        copy_f4(sDW, p.wdw[first_branch], K * DWR, G * 128);
+        publish_smem();
+    }
+    Grp g = cta_setup<G, COLS, TOT>(pipes, &tmem_slot);
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t it = 0;                                        // ring slots produced / consumed so far
+    if (warp == G * 4) {
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            for (int c = 0; c < 2 * NCH; ++c, ++it) {       // slot c of the item: channels [4c, 4c + 4)
+                const uint32_t buf = it % NB, use = it / NB;
+                if (use > 0) mbar_wait(&freeb[buf], (use - 1) & 1u);
+                publish_smem();
+                if (lane == 0) mbar_expect_tx(&fullb[buf], (uint32_t)(4 * nimg * PS * sizeof(float)));
+                __syncwarp();
+                for (int j = lane; j < 4 * nimg; j += 32) {
+                    const int ch = j & 3, i = j >> 2;
+                    bulk_g2s(X + (size_t)buf * SLOT + ch * CS + i * PS, plane_ptr(p.in[br], n0 + i, p.tin[br].c[c * 4 + ch]),
+                             (uint32_t)(PS * sizeof(float)), &fullb[buf]);
+                }
+            }
+        }
+    } else {
+        const uint32_t b_hi = smem_u32(sB), b_lo = smem_u32(sB + NP * K);
+        const float* scale = sB + 2 * NP * K;
+        const float* shift = scale + NP;
+        const int grp = threadIdx.x >> 7;
+        int loaded_branch = first_branch;
+        for (int t = blockIdx.x; t < items; t += gridDim.x) {
+            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
+            const int nimg = min(p.imgs, p.N - n0);
+            if (br != loaded_branch) {
+                group_bar(1, G * 128);
+                copy_f4(sB, p.wpw[br], WFL, G * 128);
+                copy_f4(sDW, p.wdw[br], K * DWR, G * 128);
+                publish_smem();
+                group_bar(1, G * 128);
+                loaded_branch = br;
+            }
+            const int q = grp * 128 + g.gtid;
+            const bool valid = q < HWo * nimg;
+            const int im = valid ? q / HWo : 0;
+            const int qi = valid ? q - im * HWo : 0;
+            const int oy = qi / Wout, ox = qi - oy * Wout;
+            const int woff = im * PS + (2 * oy + pad - 1) * WS + 2 * ox + pad - 1;      // window's top-left in the framed plane
+            RowSink<true, false, false> sink;
+            sink.scale = scale; sink.shift = shift; sink.valid = valid;
+            sink.obase = p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox;
+            sink.tout = p.tout[br].c; sink.sCo = (unsigned)p.out[br].sC; sink.nout = p.nout;
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                float a[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h, ++it) {
+                    const uint32_t buf = it % NB;
+                    mbar_wait(&fullb[buf], (it / NB) & 1u);
+                    dw3n<4>(X + (size_t)buf * SLOT + woff, CS, WS, sDW + (c * 8 + 4 * h) * DWR, valid, a + 4 * h);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&freeb[buf]);
+                }
+                put_chunk<K, NP>(g, a, c, b_hi, b_lo);
+            }
+            get_tile<NP>(g, sink, p.nout);
+        }
+    }
+    cta_teardown<TOT>(&tmem_slot);
+}
+
+// ===================================================================================================
 // tc_head2_kernel: tc_head_kernel with TWO pixels per thread.  The 5x5 stencil is bound by shared-memory wavefronts
 // (ncu: 48 % of the stalls are MIO throttle, 25 LDS per pixel-channel), so a thread takes a horizontally adjacent pixel
 // pair (x even): the six window columns of a row arrive as three LDS.64 and feed both pixels, the weights are loaded
@@ -1522,6 +1661,40 @@ static void dwpw_geometry(DwPwArgs& a, int Hout, size_t wfl_floats, size_t plane
 }
 
 // K=96 DW3x3(stride)->PW (+ReLU) for nbranch branches (stage-4 blocks)
+// K = 96 stride-2 depthwise -> pointwise branches on output maps of at most 512 pixels: channel-streamed whole-image items.
+// Returns YFV2_EUNSUPPORTED (without setting an error the caller reports) when the geometry does not fit; the caller falls back.
+bool tc_dws2c_supported(const Planes& in, const Planes& out, int N, int* imgs_out, int* G_out, size_t* bytes_out) {
+    const int HWo = out.H * out.W;
+    if (HWo > 4 * 128 || in.pad < 1) return false;
+    const size_t PS = (size_t)(in.H + 2 * in.pad) * in.Ws;
+    const size_t wfl = (size_t)(2 * 96 * 96 + 2 * 96) + 96 * 12;
+    int imgs = 1;
+    while ((imgs + 1) * HWo <= 4 * 128 && imgs + 1 <= N && (wfl + kDwsBufs * 4 * PS * (imgs + 1) + 4) * sizeof(float) <= kSmemCap - 2048) ++imgs;
+    const size_t bytes = (wfl + kDwsBufs * 4 * PS * imgs + 4) * sizeof(float);
+    if (bytes > kSmemCap - 2048) return false;
+    *imgs_out = imgs; *G_out = (imgs * HWo + 127) / 128; *bytes_out = bytes;
+    return true;
+}
+int tc_launch_dws2c(int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
+                    const float* const* wdw, const float* const* wpw, int N, cudaStream_t s) {
+    Dws2Args a{};
+    for (int b = 0; b < nbranch; ++b) { a.in[b] = in[b]; a.out[b] = out[b]; a.tin[b] = tin[b]; a.tout[b] = tout[b]; a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
+    a.N = N; a.nbranch = nbranch; a.nout = 96;
+    int G = 0; size_t bytes = 0;
+    if (!tc_dws2c_supported(in[0], out[0], N, &a.imgs, &G, &bytes)) { set_error("tc_launch_dws2c: unsupported geometry"); return YFV2_EUNSUPPORTED; }
+    const int items = nbranch * ((N + a.imgs - 1) / a.imgs);
+    auto run = [&](auto kern, int g) -> int {
+        TRYL(set_smem_attr(kern, bytes));
+        YFV2_CUDA(launch_k(kern, min(items, sm_count()), g * 128 + 32, bytes, s, pdl_take(), a));
+        YFV2_LAUNCH_CHECK();
+        return YFV2_OK;
+    };
+    if (G <= 1) return run(tc_dws2c_kernel<96, 96, 1>, 1);
+    if (G == 2) return run(tc_dws2c_kernel<96, 96, 2>, 2);
+    if (G == 3) return run(tc_dws2c_kernel<96, 96, 3>, 3);
+    return run(tc_dws2c_kernel<96, 96, 4>, 4);
+}
+
 int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
                      const float* const* wdw, const float* const* wpw, int N, cudaStream_t s) {
     DwPwArgs a{};

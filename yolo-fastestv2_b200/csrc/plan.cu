@@ -528,6 +528,9 @@ int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin,
                  const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s);
 int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, const ChanTab& tb, const Planes& out, const ChanTab& tout,
                  const float* wpack, int N, cudaStream_t s);
+bool tc_dws2c_supported(const Planes& in, const Planes& out, int N, int* imgs_out, int* G_out, size_t* bytes_out);
+int tc_launch_dws2c(int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
+                    const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
 int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
                      const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
 int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
@@ -670,7 +673,10 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
                     const Planes ins[2] = {in, in}; const ChanTab tins[2] = {p->tin[b], t96};
                     const Planes outs[2] = {out, out}; const ChanTab touts[2] = {p->tout[b], tmain};
                     const float* wdw[2] = {d, d + dwn + 2 * pwn}; const float* wpw[2] = {pk + p->tk_blk[b][2], pk + p->tk_blk[b][1]};
-                    TRY(tc_launch_dwpw96(2, 2, ins, tins, outs, touts, wdw, wpw, p->N, s));
+                    static const bool old_s2 = getenv("YFV2_S2_96_OLD") != nullptr;       // round-1 banded kernel, kept for A/B runs
+                    int im_ = 0, g_ = 0; size_t by_ = 0;
+                    if (!old_s2 && tc_dws2c_supported(in, out, p->N, &im_, &g_, &by_)) { TRY(tc_launch_dws2c(2, ins, tins, outs, touts, wdw, wpw, p->N, s)); }
+                    else { TRY(tc_launch_dwpw96(2, 2, ins, tins, outs, touts, wdw, wpw, p->N, s)); }
                 }
             }
         } break;
