@@ -448,7 +448,6 @@ def run_train(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    it[0] = 0
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()

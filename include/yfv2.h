@@ -126,6 +126,14 @@ YFV2_API int yfv2_decode_nms(const float* const preds[6], int N, int H, int W, i
 YFV2_API int yfv2_batch_statistics(const float* dets, const int* counts, int N, int max_det, const float* targets, int nt,
                                    float iou_threshold, float* tp, void* stream);
 
+/* ---- contrast_and_brightness (utils/datasets.py:10-16; the augmentation img_aug applies, :63-68) on the device ----
+ * out = cv2.addWeighted(img, alpha[n], zeros, 1 - alpha[n], beta[n]) for uint8 images: per byte
+ * saturate_cast<uint8>(cvRound(fl32(fl32(x * alpha) + beta))).  img / out: N images of bytes_per_image bytes each (any
+ * layout: the operation is elementwise; in place allowed); alpha / beta: device arrays [N] (the reference draws both from
+ * random.uniform(0.25, 1.75) per image on the host).  Bit-identical to OpenCV 4.x. */
+YFV2_API int yfv2_aug_contrast_brightness(const uint8_t* img, uint8_t* out, const float* alpha, const float* beta, int N,
+                                          long long bytes_per_image, void* stream);
+
 /* ---- whole inference step with HOST buffers (the evaluation() inner loop, utils/utils.py:367-383) ----
  * x_host: pinned uint8 [N,3,H,W]; out_host: pinned [N,max_det,6]; counts_host: pinned [N].
  * Copies in, runs forward_u8 + decode_nms, copies out, all on `stream`; returns without synchronising. */
@@ -175,6 +183,28 @@ YFV2_API int yfv2_op_maxpool_fwd(const float* x, float* y, int* idx, int planes,
 YFV2_API int yfv2_op_maxpool_bwd(const float* dy, const int* idx, float* dx, int planes, int H, int W, void* stream);
 YFV2_API int yfv2_op_upsample2_fwd(const float* x, float* y, int planes, int H, int W, void* stream);
 YFV2_API int yfv2_op_upsample2_bwd(const float* dy, float* dx, int planes, int H, int W, void* stream);
+
+/* ---- native training step: the train-mode forward and the backward of the WHOLE network as one call each ----------------
+ * Replaces what nn.Module.train() + autograd do for the reference's train.py:105-110 over model/detector.py:21-31 (batch-statistics
+ * BatchNorm incl. running-stat updates, ShuffleV2 shuffle / split / concat, FPN, heads, output convs).  Everything sits in a
+ * caller-owned workspace laid out at create time (activations the backward needs, their gradients, scratch); no allocation per step.
+ *   params[YFV2_NUM_PARAMS] / bn_running[2*YFV2_NUM_BN]: as yfv2_pack_weights (model.parameters() order; running_mean, running_var
+ *     per BatchNorm layer — updated in place with momentum 0.1, num_batches_tracked is the caller's).
+ *   x: fp32 [N,3,H,W].  preds[6]: the raw head tensors (written by forward; read again by backward).
+ *   dpreds[6]: d(loss)/d(preds) (e.g. from yfv2_compute_loss).  grads_flat: ONE buffer of yfv2_trainer_grad_floats() floats holding
+ *     every parameter's gradient at yfv2_trainer_param_offset(i) in parameter order (the bucket a data-parallel step all-reduces);
+ *     accumulate != 0 adds to it (gradient accumulation over sub-batches, train.py:122-124), 0 overwrites.
+ * yfv2_train_backward must follow the yfv2_train_forward of the same batch on the same workspace (and stream order). */
+typedef struct yfv2_trainer yfv2_trainer;
+YFV2_API int yfv2_trainer_create(yfv2_trainer** out, int device, int N, int H, int W, int A, int C);
+YFV2_API void yfv2_trainer_destroy(yfv2_trainer* t);
+YFV2_API int yfv2_trainer_workspace_bytes(const yfv2_trainer* t, size_t* bytes);
+YFV2_API int yfv2_trainer_grad_floats(const yfv2_trainer* t, long long* n);
+YFV2_API int yfv2_trainer_param_offset(const yfv2_trainer* t, int index, long long* offset, long long* numel);
+YFV2_API int yfv2_train_forward(yfv2_trainer* t, const float* x, const float* const* params, float* const* bn_running,
+                                float* const preds[6], void* workspace, void* stream);
+YFV2_API int yfv2_train_backward(yfv2_trainer* t, const float* x, const float* const* params, float* const preds[6],
+                                 const float* const dpreds[6], float* grads_flat, int accumulate, void* workspace, void* stream);
 
 /* ---- stage-granular forward (profiling / tests) ---------------------------------------------------------
  * A forward is a list of fused stages; yfv2_plan_stage_name(i) names them ("stem", "stage2.0", ...,

@@ -25,6 +25,7 @@ constexpr int kCPL = 8;              // classes per lane -> C <= 256
 constexpr int kChunkCells = 32;
 constexpr int kSStride = kChunkCells + 1;
 constexpr int kNmsChunk = 64;
+constexpr int kNmsListClasses = 256;   // per-class kept lists (heads + class histogram) for up to this many classes
 
 struct PostGeom {
     int N, A, C, D, M;               // D = 5+C, M = rows per image
@@ -209,6 +210,7 @@ struct NmsParams {
     int* kept_idx;     // [N,max_det] or null
     int M;             // candidate rows per image
     int MCp;           // pow2 >= M
+    int C;             // classes (per-class kept lists need C <= kNmsListClasses)
 };
 
 struct NmsSmem {
@@ -220,8 +222,13 @@ struct NmsSmem {
     float4* chbox;              // [64]
     float* charea;              // [64]
     unsigned int* cmask;        // [64][2]
-    unsigned short* kcls;       // [max_det] class of kept
-    unsigned short* chcls;      // [64]
+    // per-class kept lists: they live in the padding tail of `keys` (entries [M, MCp) are zeros once the sort is done) and in
+    // `kbox` before the first box is kept, so they cost no shared memory (one more CTA per SM matters to the scoring pass)
+    unsigned int* kcn;          // [max_det] low 16 bits: class of kept box, high 16: next kept box of that class (0xFFFF: end)
+    unsigned short* khead;      // [kNmsListClasses] newest kept box per class
+    unsigned short* chcls;      // [64] classes of the current chunk
+    unsigned int* chist;        // [kNmsListClasses] candidates per class (aliases kbox; only used before the suppression loop)
+    bool lists_fit;
     unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits, [5]=some box outside (-max_wh/2, max_wh/2)
 };
 
@@ -229,7 +236,6 @@ __host__ __device__ inline size_t nms_smem_bytes(int M, int MCp, int max_det) {
     size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (((size_t)M * 2 + 15) & ~(size_t)15);
     b += (size_t)max_det * 16 + (((size_t)max_det * 4 + 15) & ~(size_t)15);
     b += kNmsChunk * 16 + kNmsChunk * 4 + kNmsChunk * 8 + 32;
-    b += (((size_t)max_det * 2 + 15) & ~(size_t)15) + kNmsChunk * 2;
     return b;
 }
 
@@ -243,9 +249,13 @@ __device__ __forceinline__ NmsSmem carve(unsigned char* base, int M, int MCp, in
     s.chbox = reinterpret_cast<float4*>(base); base += kNmsChunk * 16;
     s.charea = reinterpret_cast<float*>(base); base += kNmsChunk * 4;
     s.cmask = reinterpret_cast<unsigned int*>(base); base += kNmsChunk * 8;
-    s.misc = reinterpret_cast<unsigned int*>(base); base += 32;
-    s.kcls = reinterpret_cast<unsigned short*>(base); base += (((size_t)max_det * 2 + 15) & ~(size_t)15);
-    s.chcls = reinterpret_cast<unsigned short*>(base);
+    s.misc = reinterpret_cast<unsigned int*>(base);
+    unsigned char* tail = reinterpret_cast<unsigned char*>(s.keys + M);
+    s.kcn = reinterpret_cast<unsigned int*>(tail); tail += (size_t)max_det * 4;
+    s.khead = reinterpret_cast<unsigned short*>(tail); tail += kNmsListClasses * 2;
+    s.chcls = reinterpret_cast<unsigned short*>(tail); tail += kNmsChunk * 2;
+    s.lists_fit = tail <= reinterpret_cast<unsigned char*>(s.keys + MCp) && (size_t)max_det * 16 >= kNmsListClasses * 4;
+    s.chist = reinterpret_cast<unsigned int*>(s.kbox);
     return s;
 }
 
@@ -383,7 +393,20 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
     const int cnt = (int)s.misc[0];
     // classes on disjoint intervals (see write_candidate) and a threshold whose rounding boundary is positive: pairs of different
     // classes have IoU exactly 0 and are skipped on their class ids
-    const bool by_class = s.misc[5] == 0u && p.iou_mid > 0.0 && p.max_wh > 0.f;
+    // ... worth it only when the candidates are spread over classes: every kept box then sits in a per-class list (newest first)
+    // and a candidate walks its own class's list instead of all kept boxes.  A single dominant class (randomly initialised
+    // heads: every candidate has the same arg-max) keeps the dense 4-way unrolled scan.
+    bool by_class = s.lists_fit && s.misc[5] == 0u && p.iou_mid > 0.0 && p.max_wh > 0.f && p.C <= kNmsListClasses;
+    if (by_class) {
+        for (int i = threadIdx.x; i < kNmsListClasses; i += NT) s.chist[i] = 0u;
+        if (threadIdx.x == 0) s.misc[6] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += NT) atomicAdd(&s.chist[s.ccls[i]], 1u);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kNmsListClasses; i += NT) if (2u * s.chist[i] > (unsigned)cnt) s.misc[6] = 1u;
+        __syncthreads();
+        by_class = s.misc[6] == 0u;
+    }
     int n2 = 64;
     while (n2 < cnt) n2 <<= 1;
     for (int i = cnt + threadIdx.x; i < n2; i += NT) s.keys[i] = 0ull;
@@ -393,6 +416,10 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
     else if (n2 == 4 * NT) bitonic_sort_desc_reg<4>(s.keys);
     else if (n2 == 8 * NT) bitonic_sort_desc_reg<8>(s.keys);
     else bitonic_sort_desc(s.keys, n2);
+    if (by_class) {                                          // the padding tail of `keys` is free from here on
+        for (int i = threadIdx.x; i < kNmsListClasses; i += NT) s.khead[i] = 0xFFFFu;
+        __syncthreads();
+    }
 
     float* out = p.out + (long long)n * p.max_det * 6;
     int* kidx = p.kept_idx ? p.kept_idx + (long long)n * p.max_det : nullptr;
@@ -409,7 +436,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
                 const float4 ob = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
                 s.chbox[t] = ob;
                 s.charea[t] = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
-                s.chcls[t] = s.ccls[slot];
+                if (by_class) s.chcls[t] = s.ccls[slot];
             }
         }
         if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }
@@ -417,13 +444,13 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
         {   // (a) chunk candidates against everything kept so far
             const int j = t & (kNmsChunk - 1), q = t / kNmsChunk;
             if (j < cn && by_class) {
+                // walk the kept boxes of this candidate's class; the candidate's four threads test every fourth node
                 const float4 bj = s.chbox[j];
                 const float aj = s.charea[j];
-                const unsigned short cj = s.chcls[j];
                 bool dead = false;
-                constexpr int STEP = NT / kNmsChunk;
-                for (int i = q; i < nk && !dead; i += STEP)
-                    if (s.kcls[i] == cj) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
+                int k = 0;
+                for (unsigned i = s.khead[s.chcls[j]]; i != 0xFFFFu && !dead; i = s.kcn[i] >> 16, ++k)
+                    if ((k & (NT / kNmsChunk - 1)) == q) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
                 if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
             } else if (j < cn) {
                 const float4 bj = s.chbox[j];
@@ -448,7 +475,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             if (i < cn) {
                 const float4 bi = s.chbox[i];
                 const float ai = s.charea[i];
-                const unsigned short ci = s.chcls[i];
+                const unsigned short ci = by_class ? s.chcls[i] : (unsigned short)0;
                 unsigned int bits = 0u;
 #pragma unroll 4
                 for (int e = 0; e < 16; ++e) {
@@ -464,10 +491,13 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             if (cn < 64) alive &= (1ull << cn) - 1ull;
             unsigned long long kept = 0ull;
             int room = p.max_det - nk;
+            int pos = nk;
             while (alive && room > 0) {
                 const int i = __ffsll((long long)alive) - 1;
                 kept |= 1ull << i;
                 --room;
+                if (by_class) { const unsigned c = s.chcls[i]; s.kcn[pos] = c | ((unsigned)s.khead[c] << 16); s.khead[c] = (unsigned short)pos; }
+                ++pos;
                 const unsigned long long m = ((unsigned long long)s.cmask[2 * i + 1] << 32) | s.cmask[2 * i];
                 alive &= ~m;
                 alive &= ~(1ull << i);
@@ -480,7 +510,6 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             const int pos = nk + __popcll(kept & ((1ull << t) - 1ull));
             s.kbox[pos] = s.chbox[t];
             s.karea[pos] = s.charea[t];
-            s.kcls[pos] = s.chcls[t];
             const unsigned long long key = s.keys[c0 + t];
             const unsigned int slot = (unsigned int)(key & 0xFFFFull);
             const float4 b = s.cbox[slot];
@@ -707,6 +736,7 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
     p.max_det = max_det; p.max_wh = max_wh; p.out = out; p.counts = counts; p.kept_idx = kept_idx; p.M = M;
     p.MCp = 64;
     while (p.MCp < M) p.MCp <<= 1;
+    p.C = 1 << 30;                                           // callers that know the class count set it
     return YFV2_OK;
 }
 }  // namespace
@@ -753,6 +783,7 @@ extern "C" int yfv2_nms(const float* dets, int N, int M, int C, float conf_thres
     NmsParams p;
     int rc = fill_nms(p, M, conf_thres, iou_thres, class_filter, n_filter, max_det, max_wh, out, counts, kept_idx);
     if (rc) return rc;
+    p.C = C;
     const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det);
     if (bytes > kSmemCap) { set_error("nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
     YFV2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -771,6 +802,7 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
     NmsParams p;
     rc = fill_nms(p, g.M, conf_thres, iou_thres, class_filter, n_filter, max_det, max_wh, out, counts, kept_idx);
     if (rc) return rc;
+    p.C = C;
     const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (size_t)(5 * A + C) * kSStride * sizeof(float);
     if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
     YFV2_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

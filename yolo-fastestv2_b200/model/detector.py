@@ -32,6 +32,7 @@ class Detector(nn.Module):
         self.output_obj_layers = nn.Conv2d(out_depth, anchor_num, 1, 1, 0, bias=True)
         self.output_cls_layers = nn.Conv2d(out_depth, classes, 1, 1, 0, bias=True)
         self._plans = {}
+        self._trainers = {}
         self._weights_gen = 0           # bumped whenever weights / BN buffers may have changed behind autograd's back
 
     # ---- weight bookkeeping ---------------------------------------------------------------------------
@@ -60,13 +61,25 @@ class Detector(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == "_plans" else copy.deepcopy(v, memo)
+            new.__dict__[k] = {} if k in ("_plans", "_trainers") else copy.deepcopy(v, memo)
         return new
 
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_plans"] = {}
+        st["_trainers"] = {}
         return st
+
+    def _trainer_for(self, x):
+        N, _, H, W = x.shape
+        key = (x.device.index, N, H, W)
+        tr = self._trainers.get(key)
+        if tr is None:
+            if len(self._trainers) >= 4:
+                self._trainers.pop(next(iter(self._trainers)))
+            tr = yfv2_engine.Trainer(x.device, N, H, W, self.anchor_num, self.classes)
+            self._trainers[key] = tr
+        return tr
 
     def _plan_for(self, x):
         N, _, H, W = x.shape
@@ -93,7 +106,12 @@ class Detector(nn.Module):
                 raise NotImplementedError("export_onnx=True is an inference-only head")
             from model import train_ops
             self.invalidate_packed()                      # the BN running statistics are updated through raw pointers
-            return train_ops.forward_train(self, x.float() if x.dtype != torch.float32 else x)
+            x = x.float() if x.dtype != torch.float32 else x
+            # default: the native trainer (csrc/trainer.cu), one C-ABI call for the forward and one for the backward;
+            # YFV2_TRAIN_PYOPS=1 keeps the op-by-op autograd composition (the path the operator tests pin)
+            if os.environ.get("YFV2_TRAIN_PYOPS") or x.shape[2] % 32 or x.shape[3] % 32:
+                return train_ops.forward_train(self, x)
+            return train_ops.forward_train_native(self, x)
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError("expected input [N,3,H,W]")
         plan = self._plan_for(x)

@@ -190,6 +190,59 @@ def _head(block, x):
     return _pw_bn(x, b[8], b[9], False)
 
 
+# ---- the whole network as ONE autograd node over the native trainer (csrc/trainer.cu) ------------------------------------------
+class NetTrainFn(torch.autograd.Function):
+    """preds = net(x) in train mode.  forward: yfv2_train_forward (saves activations in the trainer's workspace); backward:
+    yfv2_train_backward -> every parameter gradient in one flat buffer.  When the parameters' .grad already are the consecutive
+    views of one flat buffer in parameter order (train_ddp.FlatGradBucket), the gradients are ACCUMULATED straight into it and
+    autograd is told there is nothing more to add; otherwise they are returned as views of a fresh flat buffer."""
+
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        if x.requires_grad:
+            raise NotImplementedError("gradient with respect to the input image is not implemented (train.py never asks for it)")
+        tr = model._trainer_for(x)
+        _, bn = model._weight_tensors()
+        plist = [p.detach() for p in params]
+        preds = tr.forward(x, plist, bn)
+        torch._foreach_add_([m.num_batches_tracked for m in model.modules() if isinstance(m, nn.BatchNorm2d)], 1)
+        ctx.tr, ctx.gen, ctx.x, ctx.plist, ctx.preds, ctx.params = tr, tr.generation, x, plist, preds, params
+        return tuple(preds)
+
+    @staticmethod
+    def backward(ctx, *dpreds):
+        tr = ctx.tr
+        if tr.generation != ctx.gen:
+            raise RuntimeError("yfv2: the native trainer keeps ONE batch's activations per input shape; call backward() before the next "
+                               "train-mode forward of that shape (or set YFV2_TRAIN_PYOPS=1 for the op-by-op autograd path)")
+        params = ctx.params
+        # fast path: .grad tensors are the slices of one flat bucket, in order
+        base = None
+        if all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in params):
+            base = params[0].grad.data_ptr()
+            for p, (off, num) in zip(params, tr.param_offsets):
+                if p.grad.data_ptr() != base + 4 * off or p.grad.numel() != num:
+                    base = None
+                    break
+        if base is not None:
+            g0 = params[0].grad
+            flat = torch.as_strided(g0, (tr.grad_floats,), (1,), g0.storage_offset()) if g0.untyped_storage().nbytes() >= 4 * (g0.storage_offset() + tr.grad_floats) else None
+            if flat is not None:
+                tr.backward(ctx.x, ctx.plist, ctx.preds, dpreds, flat, accumulate=True)
+                return (None, None) + tuple(None for _ in params)
+        flat = torch.empty(tr.grad_floats, dtype=torch.float32, device=ctx.x.device)
+        tr.backward(ctx.x, ctx.plist, ctx.preds, dpreds, flat, accumulate=False)
+        return (None, None) + tuple(flat[off:off + num].view_as(p) for p, (off, num) in zip(params, tr.param_offsets))
+
+
+def forward_train_native(model, x):
+    """Train-mode Detector.forward through the native trainer: one autograd node for the whole network."""
+    params = list(model.parameters())
+    if not all(p.requires_grad for p in params):
+        raise NotImplementedError("the native trainer differentiates all 225 parameters; frozen parameters need YFV2_TRAIN_PYOPS=1")
+    return NetTrainFn.apply(x.contiguous(), model, *params)
+
+
 def forward_train(model, x):
     """Train-mode Detector.forward: returns the six raw head tensors with an autograd graph over our kernels."""
     bb, fpn = model.backbone, model.fpn

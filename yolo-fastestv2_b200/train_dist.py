@@ -70,6 +70,8 @@ def main(argv=None):
     ap.add_argument("--epochs", type=int, default=None, help="override cfg['epochs']")
     ap.add_argument("--max-iters", type=int, default=None, help="stop after this many iterations (smoke runs)")
     ap.add_argument("--save-dir", type=str, default="weights")
+    ap.add_argument("--device-aug", action="store_true", help="run contrast_and_brightness (utils/datasets.py:10-16) on the uint8 batch "
+                                                              "on the GPU (csrc/k_aug.cu) instead of per image in the data-loader workers")
     opt = ap.parse_args(argv)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -96,7 +98,7 @@ def main(argv=None):
         val_dataset, cf = None, collate_fn
     else:
         import utils.datasets                                                     # the reference's (not on the hot path)
-        train_dataset = utils.datasets.TensorDataset(cfg["train"], cfg["width"], cfg["height"], imgaug=True)
+        train_dataset = utils.datasets.TensorDataset(cfg["train"], cfg["width"], cfg["height"], imgaug=not opt.device_aug)
         val_dataset = utils.datasets.TensorDataset(cfg["val"], cfg["width"], cfg["height"], imgaug=False)
         cf = utils.datasets.collate_fn
     sampler = DistributedSampler(train_dataset, num_replicas=world, rank=rank, shuffle=True, drop_last=True)
@@ -130,7 +132,11 @@ def main(argv=None):
         net.train()
         sampler.set_epoch(epoch)
         for imgs, targets in train_dataloader:
-            imgs = imgs.to(device, non_blocking=True).float() / 255.0             # train.py:101
+            imgs = imgs.to(device, non_blocking=True)
+            if opt.device_aug and imgs.dtype == torch.uint8:
+                import utils.device_aug
+                imgs = utils.device_aug.img_aug_batch(imgs, out=imgs)                 # datasets.py:63-68 on the device, in place
+            imgs = imgs.float() / 255.0                                           # train.py:101
             targets = targets.to(device, non_blocking=True)
             preds = net(imgs)
             iou_loss, obj_loss, cls_loss, total_loss = utils.loss.compute_loss(preds, targets, cfg, device)

@@ -52,6 +52,7 @@ PROTOTYPES = {
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_batch_statistics": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_aug_contrast_brightness": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p]),
     "yfv2_detect_u8_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_float, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
@@ -75,6 +76,14 @@ PROTOTYPES = {
     "yfv2_op_maxpool_bwd": (ctypes.c_int, [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     "yfv2_op_upsample2_fwd": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     "yfv2_op_upsample2_bwd": (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
+    "yfv2_trainer_create": (ctypes.c_int, [_c_void_pp] + [ctypes.c_int] * 6),
+    "yfv2_trainer_destroy": (None, [ctypes.c_void_p]),
+    "yfv2_trainer_workspace_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "yfv2_trainer_grad_floats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]),
+    "yfv2_trainer_param_offset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]),
+    "yfv2_train_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_void_pp, _c_void_pp, _c_void_pp, ctypes.c_void_p, ctypes.c_void_p]),
+    "yfv2_train_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, _c_void_pp, _c_void_pp, _c_void_pp, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_void_p, ctypes.c_void_p]),
     "yfv2_plan_stage_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
     "yfv2_plan_stage_group": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yfv2_forward_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, _c_void_pp,
@@ -126,6 +135,81 @@ def _ptr_array(tensors):
 def _require_cuda(t, name):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise Yfv2Error("%s must be a CUDA tensor: this implementation has no CPU path" % name)
+
+
+class Trainer:
+    """One yfv2_trainer (the native train-mode forward + backward of the whole network) with its workspace.  The workspace keeps
+    ONE batch's activations: backward() must follow the forward() of the same batch."""
+
+    def __init__(self, device, N, H, W, A, C):
+        L = lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise Yfv2Error("trainers exist on CUDA devices only")
+        self.N, self.H, self.W, self.A, self.C = N, H, W, A, C
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(L.yfv2_trainer_create(ctypes.byref(self._h), self.device.index or 0, N, H, W, A, C), "trainer_create")
+        nb = ctypes.c_size_t()
+        _check(L.yfv2_trainer_workspace_bytes(self._h, ctypes.byref(nb)), "trainer_workspace_bytes")
+        self.workspace = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        n = ctypes.c_longlong()
+        _check(L.yfv2_trainer_grad_floats(self._h, ctypes.byref(n)), "trainer_grad_floats")
+        self.grad_floats = n.value
+        self.param_offsets = []
+        off, num = ctypes.c_longlong(), ctypes.c_longlong()
+        for i in range(225):
+            _check(L.yfv2_trainer_param_offset(self._h, i, ctypes.byref(off), ctypes.byref(num)), "trainer_param_offset")
+            self.param_offsets.append((off.value, num.value))
+        self.generation = 0                  # bumped by every forward: a backward must see the generation of its own forward
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                lib().yfv2_trainer_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    def alloc_preds(self):
+        out = []
+        for s in (16, 32):
+            h, w = self.H // s, self.W // s
+            for ch in (4 * self.A, self.A, self.C):
+                out.append(torch.empty((self.N, ch, h, w), dtype=torch.float32, device=self.device))
+        return out
+
+    @staticmethod
+    def _check_weights(params, bn_running):
+        if len(params) != 225 or len(bn_running) != 146:
+            raise Yfv2Error("trainer: expected 225 parameters and 146 BN buffers, got %d / %d" % (len(params), len(bn_running)))
+        for t in list(params) + list(bn_running):
+            _require_cuda(t, "weight")
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise Yfv2Error("trainer: weights must be contiguous float32")
+
+    def forward(self, x, params, bn_running):
+        self._check_weights(params, bn_running)
+        _require_cuda(x, "x")
+        if tuple(x.shape) != (self.N, 3, self.H, self.W) or x.dtype != torch.float32 or not x.is_contiguous():
+            raise Yfv2Error("trainer: expected a contiguous float32 input of shape %s" % ((self.N, 3, self.H, self.W),))
+        preds = self.alloc_preds()
+        with torch.cuda.device(self.device):
+            _check(lib().yfv2_train_forward(self._h, ctypes.c_void_p(x.data_ptr()), _ptr_array(params), _ptr_array(bn_running),
+                                            _ptr_array(preds), ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)),
+                   "train_forward")
+        self.generation += 1
+        return preds
+
+    def backward(self, x, params, preds, dpreds, grads_flat, accumulate):
+        if grads_flat.numel() != self.grad_floats or grads_flat.dtype != torch.float32 or not grads_flat.is_contiguous():
+            raise Yfv2Error("trainer: grads_flat must be a contiguous float32 buffer of %d elements" % self.grad_floats)
+        dp = [d.contiguous() for d in dpreds]
+        with torch.cuda.device(self.device):
+            _check(lib().yfv2_train_backward(self._h, ctypes.c_void_p(x.data_ptr()), _ptr_array(params), _ptr_array(preds), _ptr_array(dp),
+                                             ctypes.c_void_p(grads_flat.data_ptr()), int(bool(accumulate)),
+                                             ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)), "train_backward")
+        return grads_flat
 
 
 def anchors_array(cfg):
@@ -319,6 +403,27 @@ def batch_statistics(out, counts, targets, iou_threshold):
                                            ctypes.c_float(iou_threshold), ctypes.c_void_p(tp.data_ptr()), _stream(out.device)),
                "batch_statistics")
     return tp
+
+
+def contrast_and_brightness(imgs, alpha, beta, out=None):
+    """utils.datasets.contrast_and_brightness (cv2.addWeighted on uint8) for a batch on the device: imgs uint8 [N, ...],
+    alpha / beta float32 [N] (one pair per image).  Returns a new uint8 tensor (or writes `out`, which may be `imgs`)."""
+    _require_cuda(imgs, "imgs")
+    if imgs.dtype != torch.uint8:
+        raise TypeError("contrast_and_brightness expects uint8 images (the reference augments before the /255)")
+    imgs = imgs.contiguous()
+    N = imgs.shape[0]
+    alpha = torch.as_tensor(alpha, dtype=torch.float32).to(imgs.device).contiguous().reshape(-1)
+    beta = torch.as_tensor(beta, dtype=torch.float32).to(imgs.device).contiguous().reshape(-1)
+    if alpha.numel() != N or beta.numel() != N:
+        raise ValueError("one (alpha, beta) pair per image")
+    if out is None:
+        out = torch.empty_like(imgs)
+    with torch.cuda.device(imgs.device):
+        _check(lib().yfv2_aug_contrast_brightness(ctypes.c_void_p(imgs.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                                  ctypes.c_void_p(alpha.data_ptr()), ctypes.c_void_p(beta.data_ptr()), N,
+                                                  imgs.numel() // N, _stream(imgs.device)), "aug_contrast_brightness")
+    return out
 
 
 def debug_pw_tc(x, w):
