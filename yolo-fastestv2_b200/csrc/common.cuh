@@ -141,4 +141,8 @@ struct StemArgs {
 };
 int launch_stem(const StemArgs& a, cudaStream_t s);
 
+// conv1x1 backward with an optional scratch for per-block partial weight gradients (k_train.cu; the C-ABI operator passes none)
+int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, int N, int K, int M, int HW,
+                     float* wscratch, size_t wscratch_floats, cudaStream_t s);
+
 }  // namespace yfv2

@@ -375,6 +375,29 @@ __device__ __forceinline__ float dw3(const float* __restrict__ r0, const float* 
     return fmaf(d, wc.y, wc.z);
 }
 
+// Stride-2 variant for windows whose top-left is 8-byte aligned: consecutive lanes sit two floats apart, so three scalar loads per
+// window row are 2-way bank conflicted (ncu on s2c_kernel<24>: 3.2 MIO-throttle stalls per issue, 8.7 M conflicts).  The row's
+// first two taps come as ONE conflict-free LDS.64 and the third is the next lane's first tap (one shuffle); lanes whose right
+// neighbour is another row / another warp (`nb_ok` false) load it.  Same arithmetic and association as dw3: bit-identical.
+__device__ __forceinline__ float dw3_s2_shfl(const float* __restrict__ t, int WS, const float* __restrict__ wk, bool nb_ok) {
+    const float4 wa = *reinterpret_cast<const float4*>(wk);
+    const float4 wb = *reinterpret_cast<const float4*>(wk + 4);
+    const float4 wc = *reinterpret_cast<const float4*>(wk + 8);
+    float2 v[3];
+    float c2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        v[r] = *reinterpret_cast<const float2*>(t + r * WS);
+        c2[r] = __shfl_down_sync(0xffffffffu, v[r].x, 1);
+        if (!nb_ok) c2[r] = t[r * WS + 2];
+    }
+    float p0 = wa.x * v[0].x; p0 = fmaf(wa.y, v[0].y, p0); p0 = fmaf(wa.z, c2[0], p0);
+    float p1 = wa.w * v[1].x; p1 = fmaf(wb.x, v[1].y, p1); p1 = fmaf(wb.y, c2[1], p1);
+    float p2 = wb.z * v[2].x; p2 = fmaf(wb.w, v[2].y, p2); p2 = fmaf(wc.x, c2[2], p2);
+    const float d = (p0 + p1) + p2;
+    return fmaf(d, wc.y, wc.z);
+}
+
 // ===================================================================================================
 // s2c_kernel: stride-2 ShuffleV2 block (reference shufflenetv2.py:34-44,52-55), K = 24 / 48 channels per branch.
 //   proj:  dw3x3 s2 + BN on the raw input -> pw + BN + ReLU             -> output planes [0, K)
@@ -493,15 +516,19 @@ s2c_kernel(const __grid_constant__ S2cArgs p) {
             const int qc = valid ? q : 0;
             const int orow = qc / Wout, ox = qc - orow * Wout;
             const float* w0 = X + (2 * orow) * WS + 2 * ox + (pin - 1);      // window's top-left (frame column pin-1 <-> input column -1)
+            const bool aligned = (pin & 1) != 0;                               // frame of 1: every window starts on an even float
+            const bool nb_ok = ox + 1 < Wout && (threadIdx.x & 31) != 31;      // the next lane holds the pixel to the right
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 float a[KC];
                 const float* t = w0 + c * KC * RS;
                 const float* wk = sDW + c * KC * 12;
+                if (aligned) {
 #pragma unroll
-                for (int j = 0; j < KC; ++j) {
-                    a[j] = dw3<2>(t, t + WS, t + 2 * WS, wk);
-                    t += RS; wk += 12;
+                    for (int j = 0; j < KC; ++j) { a[j] = dw3_s2_shfl(t, WS, wk, nb_ok); t += RS; wk += 12; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < KC; ++j) { a[j] = dw3<2>(t, t + WS, t + 2 * WS, wk); t += RS; wk += 12; }
                 }
                 st_acquire<NB>(g);
                 st_store<KC, NB>(g, a);

@@ -205,7 +205,8 @@ int run_gemm2(const Gemm2Args& g, cudaStream_t s) {
 // quarter, four quarters of the slab side by side (a 64-wide tile would idle 6/7 of its FMAs on a 24 x 24 output).
 template <int BT>
 __global__ void __launch_bounds__(256)
-wgrad1x1_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, int N, int M, int K, int HW, int pchunk) {
+wgrad1x1_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, int N, int M, int K, int HW, int pchunk,
+                float* __restrict__ partial) {
     constexpr int BK = 32, TPT = BT / 4, SUBS = 256 / (TPT * TPT), KPS = BK / SUBS;      // threads per tile side, pixel sub-groups
     __shared__ float As[BK][BT + 1];
     __shared__ float Bs[BK][BT + 1];
@@ -247,6 +248,26 @@ wgrad1x1_kernel(const float* __restrict__ dy, const float* __restrict__ x, float
         }
         __syncthreads();
     }
+    // partial != null: this block's tile goes to its own slice partial[blockIdx.z][M][K] with plain stores (wgrad_reduce_kernel sums
+    // the slices: no atomics, deterministic); otherwise atomicAdd into the zeroed dw
+    float* dst = partial ? partial + (long long)blockIdx.z * M * K : dw;
+    if (SUBS > 1) {                                          // fold the pixel sub-groups inside the block first
+        __shared__ float red[SUBS > 1 ? SUBS - 1 : 1][BT][BT + 1];
+        if (sub > 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) red[sub - 1][ty * 4 + q][tx * 4 + r] = acc[q][r];
+        }
+        __syncthreads();
+        if (sub > 0) return;
+#pragma unroll
+        for (int u = 0; u < SUBS - 1; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[q][r] += red[u][ty * 4 + q][tx * 4 + r];
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int m = m0 + ty * 4 + q;
@@ -254,9 +275,67 @@ wgrad1x1_kernel(const float* __restrict__ dy, const float* __restrict__ x, float
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int k = k0 + tx * 4 + r;
-            if (k < K) atomicAdd(dw + (long long)m * K + k, acc[q][r]);
+            if (k < K) { if (partial) dst[(long long)m * K + k] = acc[q][r]; else atomicAdd(dst + (long long)m * K + k, acc[q][r]); }
         }
     }
+}
+
+// dw[i] = sum over the nb block slices of partial[b][i]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int nb, int MK, float* __restrict__ dw) {
+    __shared__ float red[4][64];
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63), q = threadIdx.x >> 6;
+    float v = 0.f;
+    if (i < MK) for (int b = q; b < nb; b += 4) v += partial[(long long)b * MK + i];
+    red[q][threadIdx.x & 63] = v;
+    __syncthreads();
+    if (q == 0 && i < MK) dw[i] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+}
+
+// conv1x1 wgrad for the narrowest layers (K = 24 input channels, M a multiple of 24): no shared memory, no barriers.
+// lane = pixel, a warp owns three output rows (channels m0..m0+2) and keeps 3 x KK partial sums per lane: per pixel 3 + KK
+// coalesced loads feed 3 KK FMAs; one butterfly reduction and 3 KK atomics per warp at the end of the block's pixel slice.
+// (torch.profiler: the tiled kernel above spent 170 us per 24x24 layer at 352x352 / batch 64 -- two barriers per 32 pixels for a
+// 24 x 24 output; the operands are 95 MB, 15 us of HBM time.)
+template <int KK, int RPW>
+__global__ void __launch_bounds__(24 / RPW * 32)
+wgrad_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, int N, int M, int HW, int pchunk,
+                  float* __restrict__ partial) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * 24 + warp * RPW;             // 24 rows per block (24 / RPW warps), blockIdx.y walks the 24-row groups
+    const int chunks_per_img = (HW + pchunk - 1) / pchunk;
+    const int n = blockIdx.x / chunks_per_img, p_begin = (blockIdx.x % chunks_per_img) * pchunk;
+    const int p_end = min(HW, p_begin + pchunk);
+    const float* dyp = dy + ((long long)n * M + m0) * HW;
+    const float* xp = x + (long long)n * KK * HW;
+    float acc[RPW][KK];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q)
+#pragma unroll
+        for (int k = 0; k < KK; ++k) acc[q][k] = 0.f;
+    for (int p = p_begin + lane; p < p_end; p += 32) {
+        float d[RPW];
+#pragma unroll
+        for (int q = 0; q < RPW; ++q) d[q] = __ldg(dyp + (long long)q * HW + p);
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const float v = __ldg(xp + (long long)k * HW + p);
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) acc[q][k] = fmaf(d[q], v, acc[q][k]);
+        }
+    }
+    float* dst = partial ? partial + (long long)blockIdx.x * M * KK : dw;
+#pragma unroll
+    for (int q = 0; q < RPW; ++q)
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            float v = acc[q][k];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == ((q * KK + k) & 31)) {               // spread the writers over the lanes
+                if (partial) dst[(long long)(m0 + q) * KK + k] = v; else atomicAdd(dst + (long long)(m0 + q) * KK + k, v);
+            }
+        }
 }
 
 int run_gemm(const GemmArgs& g, cudaStream_t s) {
@@ -383,7 +462,49 @@ dw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float
 // ---------------------------------------------------------------------------------------------------------------------
 // stem: dense conv 3x3 s2 p1, Cin=3 -> M
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int N, int M, int H, int W) {
+// thread = one output position, all M (<= 24) channels: the 27 input values are loaded once and reused M times, the weights come
+// from shared memory as warp-uniform float4 reads (the round-1 kernel ran one thread per output ELEMENT: 27 loads per FMA chain,
+// 0.94 ms per batch-64 launch)
+template <int MM>
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int N, int H, int W) {
+    __shared__ __align__(16) float sw[27][MM];                 // [tap = (c, ky, kx)][m]
+    for (int i = threadIdx.x; i < 27 * MM; i += 256) { const int m = i / 27, t = i - m * 27; sw[t][m] = __ldg(w + i); }
+    __syncthreads();
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)N * Ho * Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+        const long long n = i / ((long long)Wo * Ho);
+        float acc[MM];
+#pragma unroll
+        for (int m = 0; m < MM; ++m) acc[m] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = 2 * oy - 1 + ky;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = 2 * ox - 1 + kx;
+                    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+                    const float v = ok ? __ldg(x + ((n * 3 + c) * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) : 0.f;
+                    const float* wr = sw[(c * 3 + ky) * 3 + kx];
+#pragma unroll
+                    for (int m = 0; m < MM; m += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wr + m);
+                        acc[m] = fmaf(w4.x, v, acc[m]); acc[m + 1] = fmaf(w4.y, v, acc[m + 1]);
+                        acc[m + 2] = fmaf(w4.z, v, acc[m + 2]); acc[m + 3] = fmaf(w4.w, v, acc[m + 3]);
+                    }
+                }
+            }
+        float* yp = y + (n * MM) * (long long)Ho * Wo + (long long)oy * Wo + ox;
+#pragma unroll
+        for (int m = 0; m < MM; ++m) yp[(long long)m * Ho * Wo] = acc[m];
+    }
+}
+// generic fallback (any M): one thread per output element
+__global__ void stem_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int N, int M, int H, int W) {
     const int Ho = H / 2, Wo = W / 2;
     const long long total = (long long)N * M * Ho * Wo;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -405,19 +526,24 @@ __global__ void stem_fwd_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 
-// grid (M, slices): 27 partial sums per thread over (n, oy, ox), block reduce, atomicAdd
+// grid (M / 4 channel groups, slices): a thread keeps 4 x 27 partial sums over its positions (the 27 input values of a position are
+// loaded once per group of four channels instead of once per channel), block reduce, atomicAdd
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int N, int M, int H, int W) {
     const int Ho = H / 2, Wo = W / 2;
-    const int m = blockIdx.x;
-    float acc[27];
+    const int m0 = blockIdx.x * 4;
+    float acc[4][27];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc[q][t] = 0.f;
     const long long total = (long long)N * Ho * Wo;
-    for (long long q = (long long)blockIdx.y * 256 + threadIdx.x; q < total; q += (long long)gridDim.y * 256) {
-        const int ox = (int)(q % Wo), oy = (int)((q / Wo) % Ho);
-        const long long n = q / ((long long)Wo * Ho);
-        const float d = dy[((n * M + m) * Ho + oy) * Wo + ox];
+    for (long long qi = (long long)blockIdx.y * 256 + threadIdx.x; qi < total; qi += (long long)gridDim.y * 256) {
+        const int ox = (int)(qi % Wo), oy = (int)((qi / Wo) % Ho);
+        const long long n = qi / ((long long)Wo * Ho);
+        float d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[q] = m0 + q < M ? __ldg(dy + ((n * M + m0 + q) * Ho + oy) * Wo + ox) : 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -426,24 +552,30 @@ stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int ix = 2 * ox - 1 + kx;
-                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc[(c * 3 + ky) * 3 + kx] = fmaf(d, x[((n * 3 + c) * H + iy) * W + ix], acc[(c * 3 + ky) * 3 + kx]);
+                    const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+                    const float v = ok ? __ldg(x + ((n * 3 + c) * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[q][(c * 3 + ky) * 3 + kx] = fmaf(d[q], v, acc[q][(c * 3 + ky) * 3 + kx]);
                 }
             }
     }
-    __shared__ float red[8][27];
+    __shared__ float red[8][4 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-        float v = acc[t];
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp][t] = v;
-    }
+        for (int t = 0; t < 27; ++t) {
+            float v = acc[q][t];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][q * 27 + t] = v;
+        }
     __syncthreads();
-    if (threadIdx.x < 27) {
+    if (threadIdx.x < 4 * 27) {
         float v = 0.f;
         for (int wi = 0; wi < 8; ++wi) v += red[wi][threadIdx.x];
-        atomicAdd(dw + m * 27 + threadIdx.x, v);
+        const int q = threadIdx.x / 27, t = threadIdx.x - q * 27;
+        if (m0 + q < M) atomicAdd(dw + (m0 + q) * 27 + t, v);
     }
 }
 
@@ -643,11 +775,14 @@ extern "C" YFV2_API int yfv2_op_conv1x1_fwd(const float* x, const float* w, cons
     return run_gemm2(g, (cudaStream_t)stream);
 }
 // dx[n][k][p] = sum_m w[m][k] dy[n][m][p];  dw[m][k] = sum_{n,p} dy[n][m][p] x[n][k][p];  dbias[m] = sum dy
-extern "C" YFV2_API int yfv2_op_conv1x1_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, int N, int K, int M,
-                                            int HW, void* stream) {
-    ARGCHK(x && w && dy && N > 0 && K > 0 && M > 0 && HW > 0, "conv1x1_bwd: bad arguments");
-    cudaStream_t s = (cudaStream_t)stream;
+// wscratch (optional, wscratch_floats long): per-block partial weight gradients, summed by a second kernel instead of fp32 atomics
+// into dw (torch.profiler: ~150 k same-address-line atomics per 24x24 layer cost 160 us where the arithmetic needs 20).
+namespace yfv2 {
+int conv1x1_bwd_impl(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, int N, int K, int M, int HW,
+                     float* wscratch, size_t wscratch_floats, cudaStream_t s) {
+    if (!(x && w && dy && N > 0 && K > 0 && M > 0 && HW > 0)) { set_error("conv1x1_bwd: bad arguments"); return YFV2_EINVAL; }
     static const bool old_gemm = getenv("YFV2_TRAIN_GEMM_OLD") != nullptr;
+    static const bool tiled_only = getenv("YFV2_TRAIN_WGRAD_TILED") != nullptr;
     if (dx) {
         int rc;
         if (old_gemm) {
@@ -660,22 +795,35 @@ extern "C" YFV2_API int yfv2_op_conv1x1_bwd(const float* x, const float* w, cons
         if (rc) return rc;
     }
     if (dw) {
-        YFV2_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * K * sizeof(float), s));
         if (old_gemm) {
+            YFV2_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * K * sizeof(float), s));
             GemmArgs g{dy, x, dw, M, K, HW, N, HW, 1, (long long)M * HW, 1, HW, (long long)K * HW, K, 1, 0, nullptr, 1};
             int rc = run_gemm(g, s);
             if (rc) return rc;
+        } else if (K == 24 && M % 24 == 0 && !tiled_only) {      // (K = 48: 50 loads per 96 FMAs per lane measured 250 us per layer; the tiled kernel wins)
+            // pixel slices sized so that the grid has about two waves whatever the map size
+            int pchunk = 2048;
+            while (pchunk > 256 && (long long)N * (M / 24) * ((HW + pchunk - 1) / pchunk) < 2LL * sm_count()) pchunk >>= 1;
+            const int chunks = (HW + pchunk - 1) / pchunk;
+            const dim3 grid((unsigned)(N * chunks), (unsigned)(M / 24));
+            float* part = (wscratch && (size_t)N * chunks * M * K <= wscratch_floats) ? wscratch : nullptr;
+            if (!part) YFV2_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * K * sizeof(float), s));
+            wgrad_rows_kernel<24, 3><<<grid, 256, 0, s>>>(dy, x, dw, N, M, HW, pchunk, part);
+            YFV2_LAUNCH_CHECK();
+            if (part) { wgrad_reduce_kernel<<<(M * K + 63) / 64, 256, 0, s>>>(part, N * chunks, M * K, dw); YFV2_LAUNCH_CHECK(); }
         } else {
-            // pixel slices sized so that the grid has a few waves whatever the map size
             const int BT = (M <= 32 && K <= 32) ? 32 : 64;
             const int tiles = ((M + BT - 1) / BT) * ((K + BT - 1) / BT);
             int pchunk = 1024;
             while (pchunk > 64 && (long long)tiles * N * ((HW + pchunk - 1) / pchunk) < 4LL * sm_count()) pchunk >>= 1;
             const int chunks = (HW + pchunk - 1) / pchunk;
             const dim3 grid((K + BT - 1) / BT, (M + BT - 1) / BT, N * chunks);
-            if (BT == 32) wgrad1x1_kernel<32><<<grid, 256, 0, s>>>(dy, x, dw, N, M, K, HW, pchunk);
-            else wgrad1x1_kernel<64><<<grid, 256, 0, s>>>(dy, x, dw, N, M, K, HW, pchunk);
+            float* part = (wscratch && (size_t)N * chunks * M * K <= wscratch_floats) ? wscratch : nullptr;
+            if (!part) YFV2_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * K * sizeof(float), s));
+            if (BT == 32) wgrad1x1_kernel<32><<<grid, 256, 0, s>>>(dy, x, dw, N, M, K, HW, pchunk, part);
+            else wgrad1x1_kernel<64><<<grid, 256, 0, s>>>(dy, x, dw, N, M, K, HW, pchunk, part);
             YFV2_LAUNCH_CHECK();
+            if (part) { wgrad_reduce_kernel<<<(M * K + 63) / 64, 256, 0, s>>>(part, N * chunks, M * K, dw); YFV2_LAUNCH_CHECK(); }
         }
     }
     if (dbias) {
@@ -683,6 +831,11 @@ extern "C" YFV2_API int yfv2_op_conv1x1_bwd(const float* x, const float* w, cons
         YFV2_LAUNCH_CHECK();
     }
     return YFV2_OK;
+}
+}  // namespace yfv2
+extern "C" YFV2_API int yfv2_op_conv1x1_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, float* dbias, int N, int K, int M,
+                                            int HW, void* stream) {
+    return yfv2::conv1x1_bwd_impl(x, w, dy, dx, dw, dbias, N, K, M, HW, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" YFV2_API int yfv2_op_dwconv_fwd(const float* x, const float* w, float* y, int N, int C, int H, int W, int ks, int stride, void* stream) {
@@ -717,7 +870,8 @@ extern "C" YFV2_API int yfv2_op_dwconv_bwd(const float* x, const float* w, const
 
 extern "C" YFV2_API int yfv2_op_stem_fwd(const float* x, const float* w, float* y, int N, int M, int H, int W, void* stream) {
     ARGCHK(x && w && y && H % 2 == 0 && W % 2 == 0, "stem_fwd: bad arguments");
-    stem_fwd_kernel<<<grid_for((long long)N * M * (H / 2) * (W / 2)), 256, 0, (cudaStream_t)stream>>>(x, w, y, N, M, H, W);
+    if (M == 24) stem_fwd_kernel<24><<<grid_for((long long)N * (H / 2) * (W / 2)), 256, 0, (cudaStream_t)stream>>>(x, w, y, N, H, W);
+    else stem_fwd_generic_kernel<<<grid_for((long long)N * M * (H / 2) * (W / 2)), 256, 0, (cudaStream_t)stream>>>(x, w, y, N, M, H, W);
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }
@@ -725,7 +879,7 @@ extern "C" YFV2_API int yfv2_op_stem_wgrad(const float* x, const float* dy, floa
     ARGCHK(x && dy && dw, "stem_wgrad: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     YFV2_CUDA(cudaMemsetAsync(dw, 0, (size_t)M * 27 * sizeof(float), s));
-    stem_wgrad_kernel<<<dim3(M, 64), 256, 0, s>>>(x, dy, dw, N, M, H, W);
+    stem_wgrad_kernel<<<dim3((M + 3) / 4, 128), 256, 0, s>>>(x, dy, dw, N, M, H, W);
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
 }

@@ -57,7 +57,7 @@ struct yfv2_trainer {
     std::vector<long long> pnumel;
     long long ptotal = 0;
     long long ws_floats = 0;
-    long long gflat_off = 0, scratch_off = 0, pscratch_off = 0;
+    long long gflat_off = 0, scratch_off = 0, pscratch_off = 0, wscratch_off = 0;
     int x_ten = -1;
     int out_ten[6];
 };
@@ -113,6 +113,7 @@ struct Builder {
     int dw_bn(int x, const CB& c, int ks, int stride, bool relu) { return bn(dw(x, c.w, ks, stride), c, relu); }
 };
 
+constexpr long long kWScratchFloats = 4LL << 20;      // per-block partial weight gradients of one layer (16 MB)
 constexpr int kStageRepeats[3] = {4, 8, 4};
 constexpr int kStageOut[3] = {48, 96, 192};
 
@@ -230,6 +231,7 @@ void build(yfv2_trainer& t) {
     t.scratch_off = b.alloc(biggest);
     t.pscratch_off = b.alloc(pbig);
     t.gflat_off = b.alloc(t.ptotal);
+    t.wscratch_off = b.alloc(kWScratchFloats);
 }
 
 // dst[n][doff + c*dstep][p] (+)= src[n][soff + c*sstep][p],  c < count
@@ -428,7 +430,7 @@ extern "C" int yfv2_train_backward(yfv2_trainer* t, const float* x, const float*
             bool vw, vb = false; float* dw = ptarget(o.pw, &vw);
             float* db = nullptr;
             if (o.pbias >= 0) db = vw ? pscratch + t->pnumel[o.pw] : G + t->poff[o.pbias];      // bias rides behind the weight in the scratch
-            TRYT(yfv2_op_conv1x1_bwd(a, params[o.pw], dy, da, dw, db, N, A.C, o.M, A.H * A.W, s));
+            TRYT(conv1x1_bwd_impl(a, params[o.pw], dy, da, dw, db, N, A.C, o.M, A.H * A.W, P.ws + t->wscratch_off, (size_t)kWScratchFloats, s));
             if (o.pbias >= 0 && vw) { TRYT(axpy(pscratch + t->pnumel[o.pw], G + t->poff[o.pbias], t->pnumel[o.pbias], 1, s)); }
             TRYT(pcommit(o.pw, vw));
             if (o.pbias >= 0) pwritten[o.pbias] = 1;

@@ -44,6 +44,21 @@ class Detector(nn.Module):
                 bn += [m.running_mean, m.running_var]
         return params, bn
 
+    def _train_buffers(self):
+        """(running_mean / running_var list, num_batches_tracked list) for the native trainer; the module walk is cached and
+        re-done when `.to()` / `.cuda()` / load_state_dict replaced the buffer tensors."""
+        c = self.__dict__.get("_train_buf_cache")
+        first = self.backbone.first_conv[1]
+        if c is None or c[2] is not first.running_mean or c[3] is not first.num_batches_tracked:
+            bn, nbt = [], []
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    bn += [m.running_mean, m.running_var]
+                    nbt.append(m.num_batches_tracked)
+            c = (bn, nbt, first.running_mean, first.num_batches_tracked)
+            self.__dict__["_train_buf_cache"] = c
+        return c[0], c[1]
+
     def invalidate_packed(self):
         """Forces the next eval forward to re-fold BN and re-pack the weights.  Needed after edits that do not bump
         `tensor._version` (`p.data.add_()`, raw-pointer updates); `forward()` in train mode and `load_state_dict` call it."""
@@ -61,6 +76,8 @@ class Detector(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k == "_train_buf_cache":
+                continue
             new.__dict__[k] = {} if k in ("_plans", "_trainers") else copy.deepcopy(v, memo)
         return new
 
@@ -68,6 +85,7 @@ class Detector(nn.Module):
         st = dict(self.__dict__)
         st["_plans"] = {}
         st["_trainers"] = {}
+        st.pop("_train_buf_cache", None)
         return st
 
     def _trainer_for(self, x):

@@ -202,10 +202,10 @@ class NetTrainFn(torch.autograd.Function):
         if x.requires_grad:
             raise NotImplementedError("gradient with respect to the input image is not implemented (train.py never asks for it)")
         tr = model._trainer_for(x)
-        _, bn = model._weight_tensors()
+        bn, nbt = model._train_buffers()
         plist = [p.detach() for p in params]
         preds = tr.forward(x, plist, bn)
-        torch._foreach_add_([m.num_batches_tracked for m in model.modules() if isinstance(m, nn.BatchNorm2d)], 1)
+        torch._foreach_add_(nbt, 1)
         ctx.tr, ctx.gen, ctx.x, ctx.plist, ctx.preds, ctx.params = tr, tr.generation, x, plist, preds, params
         return tuple(preds)
 

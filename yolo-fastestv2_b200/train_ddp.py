@@ -14,9 +14,12 @@ class FlatGradBucket:
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)      # backward accumulates straight into the bucket
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v                                              # backward accumulates straight into the bucket
+            self.views.append(v)
             off += p.numel()
 
     def zero(self):
@@ -26,15 +29,17 @@ class FlatGradBucket:
         """`optimizer.zero_grad()` defaults to set_to_none=True since torch 2.0, which drops the views into the bucket (the
         next backward then allocates fresh .grad tensors and the all-reduce would see zeros).  Re-point every .grad at its
         slice, copying a gradient that was accumulated elsewhere."""
-        off = 0
-        for p in self.params:
-            view = self.flat[off:off + p.numel()].view_as(p)
-            if p.grad is None:
+        for p, view in zip(self.params, self.views):
+            g = p.grad
+            if g is view:                                           # the common case: nothing touched the views
+                continue
+            if g is None:
                 p.grad = view
-            elif p.grad.data_ptr() != view.data_ptr():
-                view.copy_(p.grad)
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
                 p.grad = view
-            off += p.numel()
+            else:
+                p.grad = view
 
     def allreduce_mean(self, group=None):
         self.reattach()
