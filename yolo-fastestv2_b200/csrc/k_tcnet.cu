@@ -461,6 +461,7 @@ struct HeadArgs {
     const float* wpw[2];
     float* dstA[2]; float* dstB[2]; int split[2]; int M[2];   // DENSE
     int N, imgs, nout;
+    int band_rows, bands;      // tc_head2w_kernel on large maps: an item is one band of `band_rows` rows of one image (0: whole images)
 };
 constexpr int kHeadBufs = 4;
 
@@ -1033,7 +1034,10 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
     float* sDW = sB + WFL;
     float* X = sDW + K * DWR;
     const int H = p.in[0].H, W = p.in[0].W, WS = p.in[0].Ws;
-    const int PS = (H + 4) * WS;
+    // whole images: PS = one framed plane, `imgs` of them per item.  Banded (maps of more than 256 pixel pairs): an item is
+    // band_rows rows of ONE image and PS = the band with its 2 + 2 halo rows (contiguous in the framed plane)
+    const bool banded = p.band_rows > 0;
+    const int PS = banded ? (p.band_rows + 4) * WS : (H + 4) * WS;
     const int CS = PS * p.imgs;
     const int BUF = 8 * CS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1046,7 +1050,7 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_slot, TOT);
-    const int ngroups = (p.N + p.imgs - 1) / p.imgs;
+    const int ngroups = banded ? p.N * p.bands : (p.N + p.imgs - 1) / p.imgs;
     const int items = 2 * ngroups;
     const int first_branch = (int)blockIdx.x / ngroups;
     if (threadIdx.x < G * GT) {
@@ -1061,18 +1065,21 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
     uint32_t it = 0;
     if (warp == G * 8) {
         for (int t = blockIdx.x; t < items; t += gridDim.x) {
-            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
-            const int nimg = min(p.imgs, p.N - n0);
+            const int br = t / ngroups, gi = t - br * ngroups;
+            const int n0 = banded ? gi / p.bands : gi * p.imgs;
+            const int nimg = banded ? 1 : min(p.imgs, p.N - n0);
+            const int r0 = banded ? (gi % p.bands) * p.band_rows : 0;
+            const int rows = banded ? min(p.band_rows, H - r0) : H;
+            const uint32_t bytes = (uint32_t)((rows + 4) * WS * sizeof(float));      // (whole images: the whole framed plane)
             for (int c = 0; c < NCH; ++c, ++it) {
                 const uint32_t buf = it % NB, use = it / NB;
                 if (use > 0) mbar_wait(&freeb[buf], (use - 1) & 1u);
                 publish_smem();
-                if (lane == 0) mbar_expect_tx(&fullb[buf], (uint32_t)(8 * nimg * PS * sizeof(float)));
+                if (lane == 0) mbar_expect_tx(&fullb[buf], 8u * nimg * bytes);
                 __syncwarp();
                 for (int j = lane; j < 8 * nimg; j += 32) {
                     const int ch = j & 7, i = j >> 3;
-                    bulk_g2s(X + (size_t)buf * BUF + ch * CS + i * PS, plane_ptr(p.in[br], n0 + i, c * 8 + ch),
-                             (uint32_t)(PS * sizeof(float)), &fullb[buf]);
+                    bulk_g2s(X + (size_t)buf * BUF + ch * CS + i * PS, plane_ptr(p.in[br], n0 + i, c * 8 + ch) + (size_t)r0 * WS, bytes, &fullb[buf]);
                 }
             }
         }
@@ -1088,11 +1095,14 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
         const float* scale = sB + 2 * NP * K;
         const float* shift = scale + NP;
         const int HW = H * W;
-        const int Wp = (W + 1) >> 1, PPI = H * Wp;          // pixel pairs per row / per image
+        const int Wp = (W + 1) >> 1;                        // pixel pairs per row
         int loaded_branch = first_branch;
         for (int t = blockIdx.x; t < items; t += gridDim.x) {
-            const int br = t / ngroups, n0 = (t - br * ngroups) * p.imgs;
-            const int nimg = min(p.imgs, p.N - n0);
+            const int br = t / ngroups, gi = t - br * ngroups;
+            const int n0 = banded ? gi / p.bands : gi * p.imgs;
+            const int nimg = banded ? 1 : min(p.imgs, p.N - n0);
+            const int r0 = banded ? (gi % p.bands) * p.band_rows : 0;
+            const int PPI = (banded ? min(p.band_rows, H - r0) : H) * Wp;       // pixel pairs per image of the item
             if (br != loaded_branch) {
                 group_bar(1, G * GT);
                 copy_f4(sB, p.wpw[br], WFL, G * GT);
@@ -1105,9 +1115,10 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
             const bool valid0 = q < PPI * nimg;
             const int im = valid0 ? q / PPI : 0;
             const int qi = valid0 ? q - im * PPI : 0;
-            const int oy = qi / Wp, ox = 2 * (qi - oy * Wp);
+            const int oyl = qi / Wp, ox = 2 * (qi - oyl * Wp);   // row inside the item's band
+            const int oy = r0 + oyl;
             const bool valid1 = valid0 && ox + 1 < W;
-            const int woff = im * PS + oy * WS + ox;        // even: the three LDS.64 of a window row are aligned
+            const int woff = im * PS + oyl * WS + ox;       // even: the three LDS.64 of a window row are aligned
             // sibling `sub` drains tile `sub` (the pair's pixel ox + sub)
             RowSink<false, DENSE, true> sink;
             sink.scale = scale; sink.shift = shift; sink.valid = sub ? valid1 : valid0;
@@ -1761,6 +1772,39 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
             }
             if (half == 0) return run(tc_head2w_kernel<72, 80, false>, 2 * 256 + 32);
             return run(tc_head2w_kernel<72, 96, true>, 2 * 256 + 32);
+        }
+    }
+    static const bool no_banded_heads = getenv("YFV2_HEADS_NOBANDS") != nullptr;
+    if (W % 2 == 0 && W / 2 <= 256 && !force_band && !force_g4 && !no_banded_heads) {
+        // large maps (640x640 input: 40x40): the same streamed pixel-pair kernel over bands of rows of one image
+        HeadArgs a{};
+        a.N = N; a.nout = 72; a.imgs = 1;
+        for (int b = 0; b < 2; ++b) { a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
+        if (half == 0) { a.in[0] = sIn; a.in[1] = sIn; a.out[0] = tcls; a.out[1] = treg; }
+        else {
+            a.in[0] = tcls; a.in[1] = treg;
+            a.dstA[0] = obj; a.dstB[0] = cls; a.split[0] = A; a.M[0] = A + C;
+            a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
+        }
+        const int Wp = W / 2;
+        int BR = 256 / Wp;
+        if (BR > H) BR = H;
+        const int bands = (H + BR - 1) / BR;
+        BR = (H + bands - 1) / bands;                           // equalise the bands
+        a.band_rows = BR; a.bands = (H + BR - 1) / BR;
+        const size_t PSb = (size_t)(BR + 4) * sIn.Ws;
+        const size_t wfl = (size_t)(2 * np * 72 + 2 * np) + 72 * 28;
+        const size_t bytes = (wfl + kHeadBufs * 8 * PSb + 4) * sizeof(float);
+        if (bytes <= kSmemCap - 1024) {
+            const int items = 2 * N * a.bands;
+            auto run = [&](auto kern) -> int {
+                TRYL(set_smem_attr(kern, bytes));
+                YFV2_CUDA(launch_k(kern, min(items, sm_count()), 2 * 256 + 32, bytes, s, pdl_take(), a));
+                YFV2_LAUNCH_CHECK();
+                return YFV2_OK;
+            };
+            if (half == 0) return run(tc_head2w_kernel<72, 80, false>);
+            return run(tc_head2w_kernel<72, 96, true>);
         }
     }
     if (H * W <= 512 && !force_band) {

@@ -17,6 +17,7 @@
 // The arithmetic is the training operators of k_train.cu (yfv2_op_*).  Gradients of all 225 parameters leave in ONE flat buffer in
 // parameter order (the bucket train_ddp.py all-reduces), either assigned or accumulated.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -60,6 +61,12 @@ struct yfv2_trainer {
     long long gflat_off = 0, scratch_off = 0, pscratch_off = 0, wscratch_off = 0;
     int x_ten = -1;
     int out_ten[6];
+    // CUDA-graph replay of the two static programs (~1000 launches per step otherwise: the step is host-bound at 8 GPUs): a
+    // program is captured on a private stream the first time a set of pointers is seen and replayed while they stay the same
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long key = 0; };
+    GraphSlot g_fwd, g_bwd[2];
+    cudaStream_t cap_stream = nullptr;
+    bool use_graphs = true;
 };
 
 namespace yfv2 {
@@ -309,7 +316,13 @@ extern "C" int yfv2_trainer_create(yfv2_trainer** out, int device, int N, int H,
     *out = t;
     return YFV2_OK;
 }
-extern "C" void yfv2_trainer_destroy(yfv2_trainer* t) { delete t; }
+extern "C" void yfv2_trainer_destroy(yfv2_trainer* t) {
+    if (!t) return;
+    if (t->g_fwd.exec) cudaGraphExecDestroy(t->g_fwd.exec);
+    for (auto& g : t->g_bwd) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+    delete t;
+}
 extern "C" int yfv2_trainer_workspace_bytes(const yfv2_trainer* t, size_t* bytes) {
     if (!t || !bytes) { set_error("trainer_workspace_bytes: null argument"); return YFV2_EINVAL; }
     *bytes = (size_t)t->ws_floats * sizeof(float);
@@ -339,12 +352,8 @@ struct Ptrs {
 };
 }  // namespace
 
-extern "C" int yfv2_train_forward(yfv2_trainer* t, const float* x, const float* const* params, float* const* bn_running,
-                                  float* const preds[6], void* workspace, void* stream) {
-    if (!t || !x || !params || !bn_running || !preds || !workspace) { set_error("train_forward: null argument"); return YFV2_EINVAL; }
-    for (int i = 0; i < 6; ++i) if (!preds[i]) { set_error("train_forward: null output %d", i); return YFV2_EINVAL; }
-    for (int i = 0; i < YFV2_NUM_PARAMS; ++i) if (!params[i]) { set_error("train_forward: null parameter %d", i); return YFV2_EINVAL; }
-    cudaStream_t s = (cudaStream_t)stream;
+static int run_forward(yfv2_trainer* t, const float* x, const float* const* params, float* const* bn_running,
+                       float* const preds[6], void* workspace, cudaStream_t s) {
     Ptrs P{(float*)workspace, x, preds, nullptr};
     const int N = t->N;
     for (const Op& o : t->ops) {
@@ -381,11 +390,8 @@ extern "C" int yfv2_train_forward(yfv2_trainer* t, const float* x, const float* 
     return YFV2_OK;
 }
 
-extern "C" int yfv2_train_backward(yfv2_trainer* t, const float* x, const float* const* params, float* const preds[6],
-                                   const float* const dpreds[6], float* grads_flat, int accumulate, void* workspace, void* stream) {
-    if (!t || !x || !params || !preds || !dpreds || !grads_flat || !workspace) { set_error("train_backward: null argument"); return YFV2_EINVAL; }
-    for (int i = 0; i < 6; ++i) if (!preds[i] || !dpreds[i]) { set_error("train_backward: null head tensor %d", i); return YFV2_EINVAL; }
-    cudaStream_t s = (cudaStream_t)stream;
+static int run_backward(yfv2_trainer* t, const float* x, const float* const* params, float* const preds[6],
+                        const float* const dpreds[6], float* grads_flat, int accumulate, void* workspace, cudaStream_t s) {
     Ptrs P{(float*)workspace, x, preds, dpreds};
     const int N = t->N;
     float* G = P.ws + t->gflat_off;                 // parameter gradients of this step, assigned
@@ -462,4 +468,62 @@ extern "C" int yfv2_train_backward(yfv2_trainer* t, const float* x, const float*
         if (!pwritten[i]) { set_error("train_backward: parameter %d received no gradient (internal)", (int)i); return YFV2_EINVAL; }
     TRYT(axpy(G, grads_flat, t->ptotal, accumulate ? 1 : 0, s));
     return YFV2_OK;
+}
+
+namespace {
+unsigned long long mix(unsigned long long h, const void* p) {
+    h ^= (unsigned long long)reinterpret_cast<uintptr_t>(p) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+// Replays `slot` if it was captured for `key`; otherwise captures body() on the trainer's private stream, instantiates and replays.
+template <class Body>
+int replay_or_capture(yfv2_trainer* t, yfv2_trainer::GraphSlot& slot, unsigned long long key, cudaStream_t s, Body&& body) {
+    if (!slot.exec || slot.key != key) {
+        if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+        if (!t->cap_stream) YFV2_CUDA(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+        YFV2_CUDA(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = body(t->cap_stream);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(t->cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || !graph) { set_error("trainer: stream capture failed: %s", cudaGetErrorString(e)); return YFV2_ECUDA; }
+        const cudaError_t ei = cudaGraphInstantiate(&slot.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { slot.exec = nullptr; set_error("trainer: graph instantiation failed: %s", cudaGetErrorString(ei)); return YFV2_ECUDA; }
+        slot.key = key;
+    }
+    YFV2_CUDA(cudaGraphLaunch(slot.exec, s));
+    return YFV2_OK;
+}
+}  // namespace
+
+extern "C" int yfv2_train_forward(yfv2_trainer* t, const float* x, const float* const* params, float* const* bn_running,
+                                  float* const preds[6], void* workspace, void* stream) {
+    if (!t || !x || !params || !bn_running || !preds || !workspace) { set_error("train_forward: null argument"); return YFV2_EINVAL; }
+    for (int i = 0; i < 6; ++i) if (!preds[i]) { set_error("train_forward: null output %d", i); return YFV2_EINVAL; }
+    for (int i = 0; i < YFV2_NUM_PARAMS; ++i) if (!params[i]) { set_error("train_forward: null parameter %d", i); return YFV2_EINVAL; }
+    for (int i = 0; i < 2 * YFV2_NUM_BN; ++i) if (!bn_running[i]) { set_error("train_forward: null BN buffer %d", i); return YFV2_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    static const bool no_graph = getenv("YFV2_TRAIN_NOGRAPH") != nullptr;
+    if (no_graph || !t->use_graphs) return run_forward(t, x, params, bn_running, preds, workspace, s);
+    unsigned long long key = mix(mix(0x1234ull, x), workspace);
+    for (int i = 0; i < YFV2_NUM_PARAMS; ++i) key = mix(key, params[i]);
+    for (int i = 0; i < 2 * YFV2_NUM_BN; ++i) key = mix(key, bn_running[i]);
+    for (int i = 0; i < 6; ++i) key = mix(key, preds[i]);
+    return replay_or_capture(t, t->g_fwd, key, s, [&](cudaStream_t cs) { return run_forward(t, x, params, bn_running, preds, workspace, cs); });
+}
+
+extern "C" int yfv2_train_backward(yfv2_trainer* t, const float* x, const float* const* params, float* const preds[6],
+                                   const float* const dpreds[6], float* grads_flat, int accumulate, void* workspace, void* stream) {
+    if (!t || !x || !params || !preds || !dpreds || !grads_flat || !workspace) { set_error("train_backward: null argument"); return YFV2_EINVAL; }
+    for (int i = 0; i < 6; ++i) if (!preds[i] || !dpreds[i]) { set_error("train_backward: null head tensor %d", i); return YFV2_EINVAL; }
+    for (int i = 0; i < YFV2_NUM_PARAMS; ++i) if (!params[i]) { set_error("train_backward: null parameter %d", i); return YFV2_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    static const bool no_graph = getenv("YFV2_TRAIN_NOGRAPH") != nullptr;
+    if (no_graph || !t->use_graphs) return run_backward(t, x, params, preds, dpreds, grads_flat, accumulate, workspace, s);
+    unsigned long long key = mix(mix(mix(0x4321ull, x), workspace), grads_flat);
+    for (int i = 0; i < YFV2_NUM_PARAMS; ++i) key = mix(key, params[i]);
+    for (int i = 0; i < 6; ++i) key = mix(mix(key, preds[i]), dpreds[i]);
+    return replay_or_capture(t, t->g_bwd[accumulate ? 1 : 0], key, s,
+                             [&](cudaStream_t cs) { return run_backward(t, x, params, preds, dpreds, grads_flat, accumulate, workspace, cs); });
 }

@@ -206,7 +206,7 @@ class NetTrainFn(torch.autograd.Function):
         plist = [p.detach() for p in params]
         preds = tr.forward(x, plist, bn)
         torch._foreach_add_(nbt, 1)
-        ctx.tr, ctx.gen, ctx.x, ctx.plist, ctx.preds, ctx.params = tr, tr.generation, x, plist, preds, params
+        ctx.tr, ctx.gen, ctx.plist, ctx.params = tr, tr.generation, plist, params
         return tuple(preds)
 
     @staticmethod
@@ -228,10 +228,9 @@ class NetTrainFn(torch.autograd.Function):
             g0 = params[0].grad
             flat = torch.as_strided(g0, (tr.grad_floats,), (1,), g0.storage_offset()) if g0.untyped_storage().nbytes() >= 4 * (g0.storage_offset() + tr.grad_floats) else None
             if flat is not None:
-                tr.backward(ctx.x, ctx.plist, ctx.preds, dpreds, flat, accumulate=True)
+                tr.backward(ctx.plist, dpreds, flat, accumulate=True)
                 return (None, None) + tuple(None for _ in params)
-        flat = torch.empty(tr.grad_floats, dtype=torch.float32, device=ctx.x.device)
-        tr.backward(ctx.x, ctx.plist, ctx.preds, dpreds, flat, accumulate=False)
+        flat = tr.backward(ctx.plist, dpreds, None, accumulate=False).clone()      # (autograd may keep what it is handed as .grad)
         return (None, None) + tuple(flat[off:off + num].view_as(p) for p, (off, num) in zip(params, tr.param_offsets))
 
 

@@ -162,6 +162,11 @@ class Trainer:
             _check(L.yfv2_trainer_param_offset(self._h, i, ctypes.byref(off), ctypes.byref(num)), "trainer_param_offset")
             self.param_offsets.append((off.value, num.value))
         self.generation = 0                  # bumped by every forward: a backward must see the generation of its own forward
+        # persistent buffers: the C side replays its two programs as CUDA graphs while every pointer stays the same
+        self.x_static = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.device)
+        self.preds_static = self.alloc_preds()
+        self.dpreds_static = [torch.empty_like(p) for p in self.preds_static]
+        self.flat_static = torch.empty(self.grad_floats, dtype=torch.float32, device=self.device)
 
     def __del__(self):
         try:
@@ -193,20 +198,25 @@ class Trainer:
         _require_cuda(x, "x")
         if tuple(x.shape) != (self.N, 3, self.H, self.W) or x.dtype != torch.float32 or not x.is_contiguous():
             raise Yfv2Error("trainer: expected a contiguous float32 input of shape %s" % ((self.N, 3, self.H, self.W),))
-        preds = self.alloc_preds()
+        self.x_static.copy_(x)                               # (the graph reads the batch from a fixed address)
+        preds = self.preds_static
         with torch.cuda.device(self.device):
-            _check(lib().yfv2_train_forward(self._h, ctypes.c_void_p(x.data_ptr()), _ptr_array(params), _ptr_array(bn_running),
+            _check(lib().yfv2_train_forward(self._h, ctypes.c_void_p(self.x_static.data_ptr()), _ptr_array(params), _ptr_array(bn_running),
                                             _ptr_array(preds), ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)),
                    "train_forward")
         self.generation += 1
-        return preds
+        return [p.detach() for p in preds]                   # aliases of the trainer's head buffers (overwritten by the next forward)
 
-    def backward(self, x, params, preds, dpreds, grads_flat, accumulate):
+    def backward(self, params, dpreds, grads_flat, accumulate):
+        """Backward of the last forward().  grads_flat None: the trainer's own flat buffer (overwritten) is used and returned."""
+        if grads_flat is None:
+            grads_flat, accumulate = self.flat_static, False
         if grads_flat.numel() != self.grad_floats or grads_flat.dtype != torch.float32 or not grads_flat.is_contiguous():
             raise Yfv2Error("trainer: grads_flat must be a contiguous float32 buffer of %d elements" % self.grad_floats)
-        dp = [d.contiguous() for d in dpreds]
+        torch._foreach_copy_(self.dpreds_static, [d if d.is_contiguous() else d.contiguous() for d in dpreds])
         with torch.cuda.device(self.device):
-            _check(lib().yfv2_train_backward(self._h, ctypes.c_void_p(x.data_ptr()), _ptr_array(params), _ptr_array(preds), _ptr_array(dp),
+            _check(lib().yfv2_train_backward(self._h, ctypes.c_void_p(self.x_static.data_ptr()), _ptr_array(params),
+                                             _ptr_array(self.preds_static), _ptr_array(self.dpreds_static),
                                              ctypes.c_void_p(grads_flat.data_ptr()), int(bool(accumulate)),
                                              ctypes.c_void_p(self.workspace.data_ptr()), _stream(self.device)), "train_backward")
         return grads_flat
