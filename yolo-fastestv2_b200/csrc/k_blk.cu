@@ -633,11 +633,11 @@ struct Pw3Args {
     int N, nout;
 };
 
-template <int KA, int KB, int SHA, int NP, int G, bool RELU>
+template <int KA, int KB, int SHA, int NP, int G, bool RELU, int KC = 16>
 __global__ void __launch_bounds__(G * 128, 1)
 pw3_kernel(const __grid_constant__ Pw3Args p) {
     pdl_trigger();
-    constexpr int KP = KA + KB, KC = 16, NB = 2, NCH = KP / KC;
+    constexpr int KP = KA + KB, NB = 2, NCH = KP / KC;
     constexpr int COLS = NB * 2 * KC + NP;
     static_assert(G * COLS <= 512 && KP % (2 * KC) == 0 && KA % KC == 0 && NP % 16 == 0 && KP <= kPwMaxK, "shape");
     extern __shared__ __align__(128) float smem[];
@@ -828,7 +828,7 @@ int blk_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin
     return run(s2c_kernel<48, 48, 4, 16, 2>, 4);
 }
 
-// plain pointwise; kind 0: 96->96 (+ReLU)  1: FPN S3 192->72 (+ReLU)  2: FPN S2 (up(192) ++ 96)->72 (+ReLU)
+// plain pointwise; kind 0: 96->96 (+ReLU)  1: FPN S3 192->72 (+ReLU)  2: FPN S2 (up(192) ++ 96)->72 (+ReLU)  3: 48->48 (+ReLU)
 int blk_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, const ChanTab& tb, const Planes& out, const ChanTab& tout,
                   const float* wpack, int N, cudaStream_t s) {
     Pw3Args a{};
@@ -849,6 +849,7 @@ int blk_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B,
     if (kind == 0) return run(pw3_kernel<96, 0, 0, 96, 3, true>, 96, 0, 96, 3, 96);
     if (kind == 1) return run(pw3_kernel<192, 0, 0, 80, 3, true>, 192, 0, 80, 3, 72);
     if (kind == 2) return run(pw3_kernel<192, 96, 1, 80, 3, true>, 192, 96, 80, 3, 72);
+    if (kind == 3) return run(pw3_kernel<48, 0, 0, 48, 4, true, 8>, 48, 0, 48, 4, 48);      // pw1 of the K=48 stride-2 block
     set_error("blk_launch_pw: unknown kind %d", kind);
     return YFV2_EUNSUPPORTED;
 }

@@ -1674,11 +1674,11 @@ static void dwpw_geometry(DwPwArgs& a, int Hout, size_t wfl_floats, size_t plane
 // K=96 DW3x3(stride)->PW (+ReLU) for nbranch branches (stage-4 blocks)
 // K = 96 stride-2 depthwise -> pointwise branches on output maps of at most 512 pixels: channel-streamed whole-image items.
 // Returns YFV2_EUNSUPPORTED (without setting an error the caller reports) when the geometry does not fit; the caller falls back.
-bool tc_dws2c_supported(const Planes& in, const Planes& out, int N, int* imgs_out, int* G_out, size_t* bytes_out) {
+bool tc_dws2c_supported(int K, const Planes& in, const Planes& out, int N, int* imgs_out, int* G_out, size_t* bytes_out) {
     const int HWo = out.H * out.W;
-    if (HWo > 4 * 128 || in.pad < 1) return false;
+    if (HWo > 4 * 128 || in.pad < 1 || (K != 96 && K != 48)) return false;
     const size_t PS = (size_t)(in.H + 2 * in.pad) * in.Ws;
-    const size_t wfl = (size_t)(2 * 96 * 96 + 2 * 96) + 96 * 12;
+    const size_t wfl = (size_t)(2 * K * K + 2 * K) + K * 12;
     int imgs = 1;
     while ((imgs + 1) * HWo <= 4 * 128 && imgs + 1 <= N && (wfl + kDwsBufs * 4 * PS * (imgs + 1) + 4) * sizeof(float) <= kSmemCap - 2048) ++imgs;
     const size_t bytes = (wfl + kDwsBufs * 4 * PS * imgs + 4) * sizeof(float);
@@ -1686,13 +1686,13 @@ bool tc_dws2c_supported(const Planes& in, const Planes& out, int N, int* imgs_ou
     *imgs_out = imgs; *G_out = (imgs * HWo + 127) / 128; *bytes_out = bytes;
     return true;
 }
-int tc_launch_dws2c(int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
+int tc_launch_dws2c(int K, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
                     const float* const* wdw, const float* const* wpw, int N, cudaStream_t s) {
     Dws2Args a{};
     for (int b = 0; b < nbranch; ++b) { a.in[b] = in[b]; a.out[b] = out[b]; a.tin[b] = tin[b]; a.tout[b] = tout[b]; a.wdw[b] = wdw[b]; a.wpw[b] = wpw[b]; }
-    a.N = N; a.nbranch = nbranch; a.nout = 96;
+    a.N = N; a.nbranch = nbranch; a.nout = K;
     int G = 0; size_t bytes = 0;
-    if (!tc_dws2c_supported(in[0], out[0], N, &a.imgs, &G, &bytes)) { set_error("tc_launch_dws2c: unsupported geometry"); return YFV2_EUNSUPPORTED; }
+    if (!tc_dws2c_supported(K, in[0], out[0], N, &a.imgs, &G, &bytes)) { set_error("tc_launch_dws2c: unsupported geometry"); return YFV2_EUNSUPPORTED; }
     const int items = nbranch * ((N + a.imgs - 1) / a.imgs);
     auto run = [&](auto kern, int g) -> int {
         TRYL(set_smem_attr(kern, bytes));
@@ -1700,6 +1700,12 @@ int tc_launch_dws2c(int nbranch, const Planes* in, const ChanTab* tin, const Pla
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
+    if (K == 48) {
+        if (G <= 1) return run(tc_dws2c_kernel<48, 48, 1>, 1);
+        if (G == 2) return run(tc_dws2c_kernel<48, 48, 2>, 2);
+        if (G == 3) return run(tc_dws2c_kernel<48, 48, 3>, 3);
+        return run(tc_dws2c_kernel<48, 48, 4>, 4);
+    }
     if (G <= 1) return run(tc_dws2c_kernel<96, 96, 1>, 1);
     if (G == 2) return run(tc_dws2c_kernel<96, 96, 2>, 2);
     if (G == 3) return run(tc_dws2c_kernel<96, 96, 3>, 3);

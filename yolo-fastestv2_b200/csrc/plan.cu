@@ -279,7 +279,10 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     if (!p) { set_error("plan_create: out of host memory"); return YFV2_ENOMEM; }
     memset(p, 0, sizeof(*p));
     p->device = device; p->N = N; p->H = H; p->W = W; p->A = A; p->C = C; p->training = training;
-    const int pools[4] = {24, 72, 144 + 96, 288 + 96};   // +96: scratch planes for the K=96 blocks' pw1 output
+    // + scratch planes for the pw1 output of the blocks that run pointwise-1 as its own launch: K=96 (stage 4) and, with
+    // YFV2_S2_48_SPLIT=1, the K=48 stride-2 block (stage3.0; scratch in the stride-8 pool)
+    static const bool s2_48_split = getenv("YFV2_S2_48_SPLIT") != nullptr;
+    const int pools[4] = {24, 72 + (s2_48_split ? 48 : 0), 144 + 96, 288 + 96};
     size_t off = 0;
     for (int r = 0; r < 4; ++r) {
         p->h[r] = H >> (r + 2); p->w[r] = W >> (r + 2);
@@ -335,7 +338,12 @@ extern "C" int yfv2_plan_create(yfv2_plan** out, int device, int N, int H, int W
     };
     add(0, 0, 0, "stem", 0, 0);
     for (int b = 0, st = 0, rep = 0; b < kNumBlocks; ++b) {
-        if (p->blk_K[b] < 96) add(p->blk_stride[b] == 2 ? 11 : 10, b, 0, "stage%d.%d", st + 2, rep);
+        // experiment kept behind YFV2_S2_48_SPLIT=1: the K=48 stride-2 block as pw1 to scratch planes + channel-streamed dw->pw
+        // branches (two launches, like stage4.0).  Measured 168.8 us against 139.5 us for the fused banded kernel (the extra
+        // round trip of the pointwise-1 output through L2/HBM costs more than the idle warpgroups of the fused phases).
+        if (p->blk_K[b] == 48 && p->blk_stride[b] == 2 && s2_48_split && p->h[p->blk_res[b]] * p->w[p->blk_res[b]] <= 512) {
+            add(12, b, 0, "stage%d.%d/pw1", st + 2, rep); add(13, b, 0, "stage%d.%d/dwpw", st + 2, rep);
+        } else if (p->blk_K[b] < 96) add(p->blk_stride[b] == 2 ? 11 : 10, b, 0, "stage%d.%d", st + 2, rep);
         else if (p->blk_stride[b] == 1 && tail_s1_supported(96, p->h[3], p->w[3])) add(16, b, 0, "stage%d.%d", st + 2, rep);   // small-map chain
         else { add(12, b, 0, "stage%d.%d/pw1", st + 2, rep); add(13, b, 0, "stage%d.%d/dwpw", st + 2, rep); }
         if (++rep == kStageRepeats[st]) { rep = 0; ++st; }
@@ -528,8 +536,8 @@ int tc_launch_s2(int K, const Planes& in, const Planes& out, const ChanTab& tin,
                  const float* w1, const float* wdwm, const float* w2, int N, cudaStream_t s);
 int tc_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B, const ChanTab& tb, const Planes& out, const ChanTab& tout,
                  const float* wpack, int N, cudaStream_t s);
-bool tc_dws2c_supported(const Planes& in, const Planes& out, int N, int* imgs_out, int* G_out, size_t* bytes_out);
-int tc_launch_dws2c(int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
+bool tc_dws2c_supported(int K, const Planes& in, const Planes& out, int N, int* imgs_out, int* G_out, size_t* bytes_out);
+int tc_launch_dws2c(int K, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
                     const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
 int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* tin, const Planes* out, const ChanTab* tout,
                      const float* const* wdw, const float* const* wpw, int N, cudaStream_t s);
@@ -649,34 +657,37 @@ int forward_impl(yfv2_plan* p, const void* x, int is_u8, const void* packed, flo
             TRY(tail_launch_s1(pool_planes(p, ws, p->blk_res[b]), nb, &p->tin[b], &p->tout[b], w1, wd, w2, p->N, s, &done));
             si += done - 1;
         } break;
-        case 12: case 13: {   // K=96 blocks: pw1 (global -> scratch planes), then dw3x3 -> pw2 (+ proj branch when stride 2)
-            const int stride = p->blk_stride[b];
+        case 12: case 13: {   // K=96 blocks (and the K=48 stride-2 block): pw1 (global -> scratch planes), then dw3x3 -> pw2 (+ proj branch when stride 2)
+            const int stride = p->blk_stride[b], K = p->blk_K[b];
             const Planes out = pool_planes(p, ws, p->blk_res[b]);
             const Planes in = stride == 2 ? pool_planes(p, ws, p->blk_res[b] - 1) : out;
             ChanTab t96;
-            const int base = stride == 2 ? 144 : 288;           // scratch planes live in the INPUT resolution's pool
-            for (int i = 0; i < 96; ++i) t96.c[i] = (unsigned short)(base + i);
+            // scratch planes live behind the regular planes of the INPUT resolution's pool
+            const int base = K == 48 ? 72 : (stride == 2 ? 144 : 288);
+            for (int i = 0; i < K; ++i) t96.c[i] = (unsigned short)(base + i);
             static const bool old_pw = getenv("YFV2_PW_OLD") != nullptr;          // round-1 pointwise kernel, kept for A/B runs
             if (st.kind == 12) {
-                if (old_pw) { TRY(tc_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s)); }
+                if (K == 48) { TRY(blk_launch_pw(3, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s)); }
+                else if (old_pw) { TRY(tc_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s)); }
                 else { TRY(blk_launch_pw(0, in, p->tin[b], in, p->tin[b], in, t96, pk + p->tk_blk[b][0], p->N, s)); }
             } else {
                 const float* d = pk + p->pk_block[b];
-                const int dwn = dw3_pack_floats(96), pwn = pw_pack_floats(96, 96);
+                const int dwn = dw3_pack_floats(K), pwn = pw_pack_floats(K, K);
                 if (stride == 1) {
                     const Planes ins[1] = {in}; const ChanTab tins[1] = {t96}; const Planes outs[1] = {out}; const ChanTab touts[1] = {p->tout[b]};
                     const float* wdw[1] = {d + pwn}; const float* wpw[1] = {pk + p->tk_blk[b][1]};
                     TRY(tc_launch_dwpw96(1, 1, ins, tins, outs, touts, wdw, wpw, p->N, s));
                 } else {
                     ChanTab tmain;
-                    for (int i = 0; i < 96; ++i) tmain.c[i] = p->tout[b].c[96 + i];
+                    for (int i = 0; i < K; ++i) tmain.c[i] = p->tout[b].c[K + i];
                     const Planes ins[2] = {in, in}; const ChanTab tins[2] = {p->tin[b], t96};
                     const Planes outs[2] = {out, out}; const ChanTab touts[2] = {p->tout[b], tmain};
                     const float* wdw[2] = {d, d + dwn + 2 * pwn}; const float* wpw[2] = {pk + p->tk_blk[b][2], pk + p->tk_blk[b][1]};
                     static const bool old_s2 = getenv("YFV2_S2_96_OLD") != nullptr;       // round-1 banded kernel, kept for A/B runs
                     int im_ = 0, g_ = 0; size_t by_ = 0;
-                    if (!old_s2 && tc_dws2c_supported(in, out, p->N, &im_, &g_, &by_)) { TRY(tc_launch_dws2c(2, ins, tins, outs, touts, wdw, wpw, p->N, s)); }
-                    else { TRY(tc_launch_dwpw96(2, 2, ins, tins, outs, touts, wdw, wpw, p->N, s)); }
+                    if ((K == 48 || !old_s2) && tc_dws2c_supported(K, in, out, p->N, &im_, &g_, &by_)) { TRY(tc_launch_dws2c(K, 2, ins, tins, outs, touts, wdw, wpw, p->N, s)); }
+                    else if (K == 96) { TRY(tc_launch_dwpw96(2, 2, ins, tins, outs, touts, wdw, wpw, p->N, s)); }
+                    else { set_error("forward: the K=48 stride-2 split needs an output map of at most 512 pixels"); return YFV2_EUNSUPPORTED; }
                 }
             }
         } break;
