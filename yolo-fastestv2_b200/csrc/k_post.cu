@@ -200,6 +200,7 @@ struct NmsParams {
     float conf_thres;
     double iou_thres;
     double iou_mid;    // fl32(q) > iou_thres  <=>  q > iou_mid (or >= when iou_tie_up), see iou_gt()
+    float iou_mid_f;   // (float)iou_mid: a 1e-6-wide fp32 pre-test decides almost every pair without the fp64 product
     int iou_tie_up;
     const int* class_filter;
     int n_filter;
@@ -311,6 +312,13 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& 
     if (inter == 0.f && p.iou_mid > 0.0) return false;
     const float u = __fsub_rn(__fadd_rn(aa, ab), inter);
     if (u > 0.f && u < 3.0e38f && inter < 3.0e38f) {
+        // fp32 estimate of mid*u: off by at most 2^-23 relative (rounding of mid and of the product); outside a 1e-6 band around
+        // it the exact comparison below cannot come out differently
+        const float tq = __fmul_rn(p.iou_mid_f, u);
+        if (tq > 1.0e-30f) {
+            if (inter > __fmul_rn(tq, 1.000001f)) return true;
+            if (inter < __fmul_rn(tq, 0.999999f)) return false;
+        }
         const double lhs = (double)inter, rhs = __dmul_rn(p.iou_mid, (double)u);
         return p.iou_tie_up ? lhs >= rhs : lhs > rhs;
     }
@@ -470,9 +478,12 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
                 if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
             }
         }
-        {   // (b) pairs inside the chunk: thread -> row i, 16 columns
+        __syncthreads();
+        {   // (b) pairs inside the chunk: thread -> row i, 16 columns.  Candidates that (a) already found suppressed can neither keep
+            // nor be consulted in the resolve below, so their rows and columns are skipped (most of the chunk in a crowded class)
+            const unsigned long long deadm = ((unsigned long long)s.misc[2] << 32) | s.misc[1];
             const int i = t >> 2, jq = t & 3;
-            if (i < cn) {
+            if (i < cn && !((deadm >> i) & 1ull)) {
                 const float4 bi = s.chbox[i];
                 const float ai = s.charea[i];
                 const unsigned short ci = by_class ? s.chcls[i] : (unsigned short)0;
@@ -480,7 +491,8 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
 #pragma unroll 4
                 for (int e = 0; e < 16; ++e) {
                     const int j = jq * 16 + e;
-                    if (j > i && j < cn && (!by_class || s.chcls[j] == ci) && iou_gt(bi, ai, s.chbox[j], s.charea[j], p)) bits |= 1u << e;
+                    if (j > i && j < cn && !((deadm >> j) & 1ull) && (!by_class || s.chcls[j] == ci) && iou_gt(bi, ai, s.chbox[j], s.charea[j], p))
+                        bits |= 1u << e;
                 }
                 if (bits) atomicOr(&s.cmask[2 * i + (jq >> 1)], bits << ((jq & 1) * 16));
             }
@@ -729,6 +741,7 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
         if ((double)f0 > iou_thres) f0 = nextafterf(f0, -INFINITY);
         const float f1 = nextafterf(f0, INFINITY);          // smallest float > thr
         p.iou_mid = ((double)f0 + (double)f1) * 0.5;
+        p.iou_mid_f = (float)p.iou_mid;
         unsigned int bits; memcpy(&bits, &f1, 4);
         p.iou_tie_up = (bits & 1u) == 0u;                   // ties-to-even: the midpoint rounds to f1 iff f1 is even
     }
