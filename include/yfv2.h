@@ -99,6 +99,18 @@ YFV2_API int yfv2_decode(const float* const preds[6], int N, int H, int W, int A
 YFV2_API int yfv2_export_heads(const float* const preds[6], int N, int H, int W, int A, int C, float* out2, float* out3,
                                void* stream);
 
+/* ---- deploy post-process: what yoloFastestv2::detection does after the forward (sample/ncnn/src/yolo-fastestv2.cpp) --------
+ * predHandle (:134-183: cls*obj first strict maximum above 0, grid decode in double, corners (c -/+ w/2)*scale truncated to
+ * int) + nmsHandle (:78-110: descending score, greedy, suppressed iff IoU > nms_thresh with a kept box of the SAME class;
+ * IoU on the int corners, :58-71) on the two export_onnx tensors of yfv2_export_heads.  H, W: network input size (inputHeight /
+ * inputWidth); anchors_host: 2*A*2 floats (the sample's `bias`, :34-37); scale_w/h: source image size / network input size
+ * (:189-190).  Outputs per image, descending score: boxes [N,max_out,4] int32 (x1,y1,x2,y2), scores [N,max_out], cates
+ * [N,max_out] int32, counts [N] = number kept (rows past min(count, max_out): zeros / cate -1; the sample has no cap, so pass
+ * max_out = A*(H/16*W/16 + H/32*W/32) to never truncate).  Equal scores keep push order (the sample's std::sort leaves it open). */
+YFV2_API int yfv2_ncnn_post(const float* out2, const float* out3, int N, int H, int W, int A, int C, const float* anchors_host,
+                            float thresh, float nms_thresh, float scale_w, float scale_h, int max_out, int* boxes, float* scores,
+                            int* cates, int* counts, void* stream);
+
 /* ---- non_max_suppression (utils/utils.py:232-296) + torchvision.ops.nms ------------------------------
  * dets: [N,M,5+C].  out: [N,max_det,6] rows (x1,y1,x2,y2,conf,cls) by descending conf; counts: [N];
  * kept_idx (optional, may be NULL): [N,max_det] row index into dets[n].  class_filter: n_filter device
@@ -230,6 +242,11 @@ YFV2_API int yfv2_debug_gather(const yfv2_plan* plan, const void* workspace, int
  * x: [K][P], w: [N][K], out: [N][P], pack_ws: scratch of at least 2*roundup(N,16)*roundup(K,8) floats. */
 YFV2_API int yfv2_debug_pw_tc(const float* x, const float* w, float* out, float* pack_ws, int K, int N, int P,
                               void* stream);
+
+/* ---- profiling hook: yfv2_decode_nms runs an instrumented kernel while dev_buf != NULL and writes, per image, 16 int64:
+ * clock64 ticks of [0] candidate generation, [1] sort, [2] chunk load, [3] chunk vs kept, [4] pairs inside the chunk,
+ * [5] serial resolve, [6] append, [7] tail; [8] chunks, [9] candidates, [10] kept.  dev_buf: N x 16 int64 on the device. */
+YFV2_API int yfv2_debug_nms_profile(long long* dev_buf);
 
 #ifdef __cplusplus
 }

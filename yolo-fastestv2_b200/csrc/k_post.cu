@@ -212,6 +212,8 @@ struct NmsParams {
     int M;             // candidate rows per image
     int MCp;           // pow2 >= M
     int C;             // classes (per-class kept lists need C <= kNmsListClasses)
+    int variant;       // 1: dense chunk-vs-kept pass with a warp per 8 candidates (see sort_and_suppress)
+    long long* prof;   // yfv2_debug_nms_profile: per image 16 x int64 (clock64 ticks per phase), else null
 };
 
 struct NmsSmem {
@@ -396,8 +398,19 @@ __device__ void bitonic_sort_desc_reg(unsigned long long* keys) {
 }
 
 // Sort the pushed candidates and run the blocked greedy suppression.  All threads of the CTA call this.
-__device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
+// PROF (debug builds of the kernels, yfv2_debug_nms_profile): thread 0 accumulates clock64 ticks per phase; `tstart` is the
+// kernel's first timestamp.  Phases: 0 candidate generation, 1 class histogram + sort, 2 chunk load, 3 chunk vs kept, 4 pairs
+// inside the chunk, 5 serial resolve, 6 append, 7 tail; [8] chunks, [9] candidates.
+template <bool PROF>
+__device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, long long tstart = 0) {
+    long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = tstart;
+    int nchunks = 0;
+    auto tick = [&](int k) {
+        if (PROF && threadIdx.x == 0) { const long long tn = clock64(); acc[k] += tn - tlast; tlast = tn; }
+    };
     __syncthreads();
+    tick(0);
     const int cnt = (int)s.misc[0];
     // classes on disjoint intervals (see write_candidate) and a threshold whose rounding boundary is positive: pairs of different
     // classes have IoU exactly 0 and are skipped on their class ids
@@ -428,6 +441,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
         for (int i = threadIdx.x; i < kNmsListClasses; i += NT) s.khead[i] = 0xFFFFu;
         __syncthreads();
     }
+    tick(1);
 
     float* out = p.out + (long long)n * p.max_det * 6;
     int* kidx = p.kept_idx ? p.kept_idx + (long long)n * p.max_det : nullptr;
@@ -449,6 +463,8 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
         }
         if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }
         __syncthreads();
+        tick(2);
+        ++nchunks;
         {   // (a) chunk candidates against everything kept so far
             const int j = t & (kNmsChunk - 1), q = t / kNmsChunk;
             if (j < cn && by_class) {
@@ -460,6 +476,38 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
                 for (unsigned i = s.khead[s.chcls[j]]; i != 0xFFFFu && !dead; i = s.kcn[i] >> 16, ++k)
                     if ((k & (NT / kNmsChunk - 1)) == q) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
                 if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
+            } else if (p.variant == 1) {
+                // dense set, transposed: a warp owns 8 of the chunk's candidates and walks the kept boxes 32 at a time, lane = kept box
+                // (two conflict-free loads per block instead of two per test), candidate = broadcast load.  A candidate leaves the walk
+                // at the first block that suppresses it (warp vote), so the ~3/4 of a crowded chunk that die stop costing tests; the
+                // lane-per-candidate scan below only ends when its last surviving lane has seen every kept box.  Same tests, same result.
+                const int wp = t >> 5, ln = t & 31;
+                constexpr int CPW = kNmsChunk / (NT / 32);
+                unsigned alive = 0u;
+#pragma unroll
+                for (int jj = 0; jj < CPW; ++jj) if (wp * CPW + jj < cn) alive |= 1u << jj;
+                const unsigned mine = alive;
+                for (int kb = 0; kb < nk && alive; kb += 32) {
+                    const int i = kb + ln;
+                    const bool vi = i < nk;
+                    const float4 kx = s.kbox[vi ? i : 0];
+                    const float ka = s.karea[vi ? i : 0];
+                    unsigned m = alive;
+                    while (m) {
+                        const int j0 = __ffs((int)m) - 1;
+                        m &= m - 1u;
+                        const int j1 = m ? __ffs((int)m) - 1 : j0;       // second candidate of the trip (independent chain)
+                        m &= m - 1u;                                       // (0 & anything stays 0)
+                        const float4 b0 = s.chbox[wp * CPW + j0], b1 = s.chbox[wp * CPW + j1];
+                        const float a0 = s.charea[wp * CPW + j0], a1 = s.charea[wp * CPW + j1];
+                        const bool d0 = vi && iou_gt(kx, ka, b0, a0, p);
+                        const bool d1 = vi && iou_gt(kx, ka, b1, a1, p);
+                        if (__any_sync(0xffffffffu, d0)) alive &= ~(1u << j0);
+                        if (__any_sync(0xffffffffu, d1)) alive &= ~(1u << j1);
+                    }
+                }
+                const unsigned deadb = mine & ~alive;
+                if (ln == 0 && deadb) atomicOr(&s.misc[1 + (wp * CPW >> 5)], deadb << ((wp * CPW) & 31));
             } else if (j < cn) {
                 const float4 bj = s.chbox[j];
                 const float aj = s.charea[j];
@@ -479,6 +527,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             }
         }
         __syncthreads();
+        tick(3);
         {   // (b) pairs inside the chunk: thread -> row i, 16 columns.  Candidates that (a) already found suppressed can neither keep
             // nor be consulted in the resolve below, so their rows and columns are skipped (most of the chunk in a crowded class)
             const unsigned long long deadm = ((unsigned long long)s.misc[2] << 32) | s.misc[1];
@@ -498,6 +547,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             }
         }
         __syncthreads();
+        tick(4);
         if (t == 0) {   // (c) serial resolve
             unsigned long long alive = ~(((unsigned long long)s.misc[2] << 32) | s.misc[1]);
             if (cn < 64) alive &= (1ull << cn) - 1ull;
@@ -517,6 +567,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
             s.misc[3] = (unsigned int)kept; s.misc[4] = (unsigned int)(kept >> 32);
         }
         __syncthreads();
+        tick(5);
         const unsigned long long kept = ((unsigned long long)s.misc[4] << 32) | s.misc[3];
         if (t < cn && ((kept >> t) & 1ull)) {   // (d) append
             const int pos = nk + __popcll(kept & ((1ull << t) - 1ull));
@@ -533,10 +584,20 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n) {
         }
         nk += __popcll(kept);
         __syncthreads();
+        tick(6);
     }
     if (t == 0) p.counts[n] = nk;
     for (int i = nk * 6 + t; i < p.max_det * 6; i += NT) out[i] = 0.f;
     if (kidx) for (int i = nk + t; i < p.max_det; i += NT) kidx[i] = -1;
+    if (PROF) {
+        __syncthreads();
+        tick(7);
+        if (t == 0 && p.prof) {
+            long long* q = p.prof + (long long)n * 16;
+            for (int k = 0; k < 8; ++k) q[k] = acc[k];
+            q[8] = nchunks; q[9] = cnt; q[10] = nk;
+        }
+    }
 }
 
 // NMS from an [N,M,5+C] tensor: one CTA per image, warp per row for the scoring pass.
@@ -566,7 +627,7 @@ nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
             write_candidate(s, slot, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r, p.max_wh);
         }
     }
-    sort_and_suppress(s, p, n);
+    sort_and_suppress<false>(s, p, n);
 }
 
 // Fused: candidates come straight from the head logits.
@@ -649,9 +710,11 @@ __device__ __forceinline__ void thread_cell_candidates(const PostGeom& g, const 
     }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(NT, 2)
 decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
     pdl_wait();
+    const long long tstart = PROF ? clock64() : 0ll;
     extern __shared__ __align__(16) unsigned char smraw[];
     const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
     float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
@@ -669,7 +732,7 @@ decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
                 thread_cell_candidates(g, p, s, n, lv, in_range ? cell : 0, in_range, row0);
             }
         }
-        sort_and_suppress(s, p, n);
+        sort_and_suppress<PROF>(s, p, n, tstart);
         return;
     }
     for (int lv = 0; lv < 2; ++lv) {
@@ -706,8 +769,10 @@ decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
             }
         }
     }
-    sort_and_suppress(s, p, n);
+    sort_and_suppress<PROF>(s, p, n, tstart);
 }
+
+long long* g_nms_prof = nullptr;       // yfv2_debug_nms_profile
 
 int fill_geom(PostGeom& g, const float* const preds[6], int N, int H, int W, int A, int C, const double* anchors_host) {
     if (!preds || !anchors_host || N <= 0 || A <= 0 || A > kMaxA || C <= 0 || C > 32 * kCPL || H % 32 || W % 32 || H <= 0 || W <= 0) {
@@ -750,6 +815,9 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
     p.MCp = 64;
     while (p.MCp < M) p.MCp <<= 1;
     p.C = 1 << 30;                                           // callers that know the class count set it
+    p.prof = nullptr;
+    static const int variant = getenv("YFV2_NMS_V") ? atoi(getenv("YFV2_NMS_V")) : 0;
+    p.variant = variant;
     return YFV2_OK;
 }
 }  // namespace
@@ -818,7 +886,9 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
     p.C = C;
     const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (size_t)(5 * A + C) * kSStride * sizeof(float);
     if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
-    YFV2_CUDA(cudaFuncSetAttribute(decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    p.prof = g_nms_prof;
+    auto kern = p.prof ? decode_nms_kernel<true> : decode_nms_kernel<false>;
+    YFV2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     {   // nothing is read before pdl_wait(), so overlapping the predecessor's tail is always safe
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)N); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = bytes; cfg.stream = (cudaStream_t)stream;
@@ -827,8 +897,15 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = pdl_allowed() ? 1 : 0;
         const int fast = (C <= kCT && !getenv("YFV2_NMS_WARP_PER_CELL")) ? 1 : 0;
-        YFV2_CUDA(cudaLaunchKernelEx(&cfg, decode_nms_kernel, g, p, fast));
+        YFV2_CUDA(cudaLaunchKernelEx(&cfg, kern, g, p, fast));
     }
     YFV2_LAUNCH_CHECK();
+    return YFV2_OK;
+}
+
+/* test / profiling hook: per-image clock64 ticks of the phases of decode_nms_kernel (see sort_and_suppress).  `dev_buf`: N x 16
+ * int64 on the device, or NULL to switch the instrumented kernel off again.  Process-wide; not for concurrent use. */
+extern "C" int yfv2_debug_nms_profile(long long* dev_buf) {
+    g_nms_prof = dev_buf;
     return YFV2_OK;
 }

@@ -17,6 +17,10 @@
 // Staging: planes live in global memory inside zero frames (common.cuh), so the rows a band needs, halo and
 // padding included, are one contiguous 16-byte-aligned run per plane: one TMA bulk copy (cp.async.bulk, UBLKCP)
 // per plane, issued by K different threads, completion counted on an mbarrier.  No per-element address math.
+#include <string.h>
+
+#include <vector>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -462,6 +466,12 @@ struct HeadArgs {
     float* dstA[2]; float* dstB[2]; int split[2]; int M[2];   // DENSE
     int N, imgs, nout;
     int band_rows, bands;      // tc_head2w_kernel on large maps: an item is one band of `band_rows` rows of one image (0: whole images)
+    // tc_head2w_kernel, whole-image items: pixel pair of thread q of the item as (image << 16 | row << 8 | pair column), 0xFFFFFFFF:
+    // idle lane.  Raster order makes every half-warp of the stencil's LDS.64 window loads 2-way bank conflicted (a half-warp spans
+    // two framed rows whose bank ranges overlap; ncu: 9.2 M conflict wavefronts per launch); build_lanemap() deals the pairs so that
+    // the 16 lanes of a half-warp sit in 16 different 8-byte banks.
+    int use_map;
+    unsigned int lanemap[256];
 };
 constexpr int kHeadBufs = 4;
 
@@ -1112,10 +1122,19 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
                 loaded_branch = br;
             }
             const int q = grp * 128 + g.gtid;               // pair index inside the item
-            const bool valid0 = q < PPI * nimg;
-            const int im = valid0 ? q / PPI : 0;
-            const int qi = valid0 ? q - im * PPI : 0;
-            const int oyl = qi / Wp, ox = 2 * (qi - oyl * Wp);   // row inside the item's band
+            bool valid0;
+            int im, oyl, ox;                                // oyl: row inside the item's band
+            if (p.use_map) {
+                const unsigned int e = p.lanemap[q];
+                im = (int)(e >> 16); oyl = (int)((e >> 8) & 0xFFu); ox = 2 * (int)(e & 0xFFu);
+                valid0 = e != 0xFFFFFFFFu && im < nimg;
+                if (!valid0) { im = 0; oyl = 0; ox = 0; }
+            } else {
+                valid0 = q < PPI * nimg;
+                im = valid0 ? q / PPI : 0;
+                const int qi = valid0 ? q - im * PPI : 0;
+                oyl = qi / Wp; ox = 2 * (qi - oyl * Wp);
+            }
             const int oy = r0 + oyl;
             const bool valid1 = valid0 && ox + 1 < W;
             const int woff = im * PS + oyl * WS + ox;       // even: the three LDS.64 of a window row are aligned
@@ -1735,6 +1754,41 @@ int tc_launch_dwpw96(int stride, int nbranch, const Planes* in, const ChanTab* t
 
 // heads: half 0: T = BN(pw(ReLU(BN(dw5x5(S)))));  half 1: preds = F(ReLU(BN(dw5x5(T)))) with F = outconv o BN o pw folded
 // into one [M x 72] matrix + bias at pack time (plan.cu).  branch 0 = cls head (outputs obj+cls), branch 1 = reg head.
+// Deal the H x ceil(W/2) pixel pairs of `imgs` framed planes (row stride WS, plane stride PS floats) to 256 lanes so that the 16
+// lanes of every half-warp read 16 different 8-byte shared-memory banks: bank unit of a pair = (offset / 2) mod 16, the window
+// taps shift all lanes alike.  Greedy in raster order (keeps a half-warp's pairs close together for the epilogue's stores);
+// pairs that cannot be placed conflict-free (a residue class with more than 16 members) fill the remaining lanes.
+static void build_lanemap(HeadArgs& a, int H, int W, int WS, int imgs, size_t PS) {
+    const int Wp = (W + 1) / 2, total = imgs * H * Wp;
+    static thread_local int key[5] = {0, 0, 0, 0, 0};
+    static thread_local unsigned int cached[256];
+    if (key[0] != H || key[1] != W || key[2] != WS || key[3] != imgs || key[4] != (int)PS) {
+        std::vector<unsigned int> pend((size_t)total), rest;
+        for (int i = 0; i < total; ++i) {
+            const int im = i / (H * Wp), r = (i / Wp) % H, j = i % Wp;
+            pend[(size_t)i] = ((unsigned)im << 16) | ((unsigned)r << 8) | (unsigned)j;
+        }
+        auto unit = [&](unsigned int e) { return (int)((((size_t)(e >> 16) * PS + (size_t)((e >> 8) & 0xFFu) * WS + 2 * (size_t)(e & 0xFFu)) / 2) % 16); };
+        for (int i = 0; i < 256; ++i) cached[i] = 0xFFFFFFFFu;
+        for (int h = 0; h < 16; ++h) {
+            bool used[16] = {false};
+            int got = 0;
+            rest.clear();
+            for (unsigned int e : pend) {
+                const int u = unit(e);
+                if (got < 16 && !used[u]) { used[u] = true; cached[16 * h + got++] = e; }
+                else rest.push_back(e);
+            }
+            pend.swap(rest);
+        }
+        for (int i = 0; i < 256 && !pend.empty(); ++i)
+            if (cached[i] == 0xFFFFFFFFu) { cached[i] = pend.back(); pend.pop_back(); }
+        key[0] = H; key[1] = W; key[2] = WS; key[3] = imgs; key[4] = (int)PS;
+    }
+    memcpy(a.lanemap, cached, sizeof(cached));
+    a.use_map = 1;
+}
+
 int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
                     float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s) {
     if (A + C > 96 || 4 * A > 96) { set_error("tc heads: A+C=%d exceeds the output tile (96)", A + C); return YFV2_EUNSUPPORTED; }
@@ -1763,6 +1817,8 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         while ((a.imgs + 1) * PPI <= 256 && a.imgs + 1 <= N &&
                (wfl + kHeadBufs * 8 * PS * (a.imgs + 1) + 4) * sizeof(float) <= kSmemCap - 1024) ++a.imgs;
         const size_t bytes = (wfl + kHeadBufs * 8 * PS * a.imgs + 4) * sizeof(float);
+        static const bool raster_heads = getenv("YFV2_HEADS_RASTER") != nullptr;      // A/B: raster lane order (bank conflicted)
+        if (!raster_heads && H < 256 && W / 2 < 256 && a.imgs < 0xFFFF) build_lanemap(a, H, W, sIn.Ws, a.imgs, PS);
         if (bytes <= kSmemCap - 1024) {
             const int ngroups = (N + a.imgs - 1) / a.imgs;
             static const bool old_heads = getenv("YFV2_HEADS_OLD") != nullptr;     // round-1 kernel (one warp per lane quarter), kept for A/B runs

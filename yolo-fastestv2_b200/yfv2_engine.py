@@ -92,6 +92,10 @@ PROTOTYPES = {
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "yfv2_debug_gather": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "yfv2_debug_nms_profile": (ctypes.c_int, [ctypes.c_void_p]),
+    "yfv2_ncnn_post": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_float), ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 
@@ -520,3 +524,39 @@ def export_heads(preds):
         _check(lib().yfv2_export_heads(_ptr_array(preds), N, h * 16, w * 16, A, C, ctypes.c_void_p(o2.data_ptr()),
                                        ctypes.c_void_p(o3.data_ptr()), _stream(dev)), "export_heads")
     return o2, o3
+
+
+NCNN_ANCHORS = (12.64, 19.39, 37.88, 51.48, 55.71, 138.31, 126.91, 78.23, 131.57, 214.55, 279.92, 258.87)   # sample/ncnn/src/yolo-fastestv2.cpp:34-35
+
+
+def ncnn_post(out2, out3, anchor_num, thresh=0.3, nms_thresh=0.25, src_size=None, anchors=NCNN_ANCHORS, max_out=None):
+    """The deploy post-process of the reference's ncnn sample (yoloFastestv2::detection after the forward: predHandle + nmsHandle,
+    sample/ncnn/src/yolo-fastestv2.cpp:78-183) on the export_onnx tensors `out2` [N,h,w,5A+C], `out3` (export_heads above).
+    src_size = (cols, rows) of the source image (default: the network input size, scale 1).  Returns a list of N tuples
+    (boxes int32 [n,4], scores float32 [n], cates int32 [n]) on the CPU, descending score, like the sample's dstBoxes."""
+    if not (out2.is_cuda and out3.is_cuda):
+        raise RuntimeError("yfv2: ncnn_post needs CUDA tensors (there is no CPU fallback)")
+    out2 = out2.detach().contiguous().float(); out3 = out3.detach().contiguous().float()
+    N, h, w, ch = out2.shape
+    A = int(anchor_num)
+    C = ch - 5 * A
+    H, W = h * 16, w * 16
+    M = A * (h * w + out3.shape[1] * out3.shape[2])
+    max_out = M if max_out is None else int(max_out)
+    sw, sh = (W, H) if src_size is None else src_size
+    import numpy as np
+    scale_w = float(np.float32(sw) / np.float32(W)); scale_h = float(np.float32(sh) / np.float32(H))        # :189-190, float division
+    dev = out2.device
+    boxes = torch.empty((N, max_out, 4), dtype=torch.int32, device=dev)
+    scores = torch.empty((N, max_out), dtype=torch.float32, device=dev)
+    cates = torch.empty((N, max_out), dtype=torch.int32, device=dev)
+    counts = torch.empty((N,), dtype=torch.int32, device=dev)
+    anc = (ctypes.c_float * (4 * A))(*[float(a) for a in anchors][:4 * A])
+    with torch.cuda.device(dev):
+        _check(lib().yfv2_ncnn_post(ctypes.c_void_p(out2.data_ptr()), ctypes.c_void_p(out3.data_ptr()), N, H, W, A, C, anc,
+                                    ctypes.c_float(thresh), ctypes.c_float(nms_thresh), ctypes.c_float(scale_w), ctypes.c_float(scale_h),
+                                    max_out, ctypes.c_void_p(boxes.data_ptr()), ctypes.c_void_p(scores.data_ptr()),
+                                    ctypes.c_void_p(cates.data_ptr()), ctypes.c_void_p(counts.data_ptr()), _stream(dev)), "ncnn_post")
+    cnt = counts.cpu().tolist()
+    b, s, c = boxes.cpu(), scores.cpu(), cates.cpu()
+    return [(b[i, :min(cnt[i], max_out)].numpy(), s[i, :min(cnt[i], max_out)].numpy(), c[i, :min(cnt[i], max_out)].numpy()) for i in range(N)]
