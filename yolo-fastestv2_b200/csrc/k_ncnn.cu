@@ -52,7 +52,7 @@ struct Smem {
 };
 
 __host__ __device__ inline size_t smem_bytes(int M, int MCp) {
-    size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (size_t)M * 4;
+    size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (((size_t)M * 4 + 15) & ~(size_t)15);
     b += (((size_t)M * 2 + 15) & ~(size_t)15) * 2;
     b += kChunk * 16 + kChunk * 4 + (((size_t)kChunk * 2 + 15) & ~(size_t)15) + kChunk * 8 + 32;
     return b;
@@ -62,7 +62,7 @@ __device__ __forceinline__ Smem carve(unsigned char* p, int M, int MCp) {
     Smem s;
     s.keys = reinterpret_cast<unsigned long long*>(p); p += (size_t)MCp * 8;
     s.box = reinterpret_cast<int4*>(p); p += (size_t)M * 16;
-    s.area = reinterpret_cast<float*>(p); p += (size_t)M * 4;
+    s.area = reinterpret_cast<float*>(p); p += (((size_t)M * 4 + 15) & ~(size_t)15);
     s.cate = reinterpret_cast<short*>(p); p += (((size_t)M * 2 + 15) & ~(size_t)15);
     s.picked = reinterpret_cast<unsigned short*>(p); p += (((size_t)M * 2 + 15) & ~(size_t)15);
     s.chbox = reinterpret_cast<int4*>(p); p += kChunk * 16;

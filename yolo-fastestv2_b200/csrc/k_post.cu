@@ -201,6 +201,8 @@ struct NmsParams {
     double iou_thres;
     double iou_mid;    // fl32(q) > iou_thres  <=>  q > iou_mid (or >= when iou_tie_up), see iou_gt()
     float iou_mid_f;   // (float)iou_mid: a 1e-6-wide fp32 pre-test decides almost every pair without the fp64 product
+    float iou_fast_mid;  // iou_fast(): iou_mid_f, or NaN when iou_mid <= 0 (every pair then takes the exact path)
+    float iou_zero;      // iou_fast(): 0 (an empty intersection is below a positive threshold), or NaN when iou_mid <= 0
     int iou_tie_up;
     const int* class_filter;
     int n_filter;
@@ -212,7 +214,6 @@ struct NmsParams {
     int M;             // candidate rows per image
     int MCp;           // pow2 >= M
     int C;             // classes (per-class kept lists need C <= kNmsListClasses)
-    int variant;       // 1: dense chunk-vs-kept pass with a warp per 8 candidates (see sort_and_suppress)
     long long* prof;   // yfv2_debug_nms_profile: per image 16 x int64 (clock64 ticks per phase), else null
 };
 
@@ -222,23 +223,24 @@ struct NmsSmem {
     unsigned short* ccls;       // [M]
     float4* kbox;               // [max_det] offset boxes of kept
     float* karea;               // [max_det]
-    float4* chbox;              // [64]
-    float* charea;              // [64]
-    unsigned int* cmask;        // [64][2]
+    float4* chbox;              // [2][64]  double buffered: chunk c in buffer c & 1
+    float* charea;              // [2][64]
+    unsigned int* cmask;        // [64][2]  kill rows of the chunk's candidates
+    unsigned char* alist;       // [64]     chunk indices of the candidates alive after (a), in order
     // per-class kept lists: they live in the padding tail of `keys` (entries [M, MCp) are zeros once the sort is done) and in
     // `kbox` before the first box is kept, so they cost no shared memory (one more CTA per SM matters to the scoring pass)
     unsigned int* kcn;          // [max_det] low 16 bits: class of kept box, high 16: next kept box of that class (0xFFFF: end)
     unsigned short* khead;      // [kNmsListClasses] newest kept box per class
-    unsigned short* chcls;      // [64] classes of the current chunk
+    unsigned short* chcls;      // [2][64] classes of the staged chunks
     unsigned int* chist;        // [kNmsListClasses] candidates per class (aliases kbox; only used before the suppression loop)
     bool lists_fit;
-    unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits, [5]=some box outside (-max_wh/2, max_wh/2)
+    unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits, [5]=some box outside (-max_wh/2, max_wh/2), [6] scratch
 };
 
 __host__ __device__ inline size_t nms_smem_bytes(int M, int MCp, int max_det) {
     size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (((size_t)M * 2 + 15) & ~(size_t)15);
     b += (size_t)max_det * 16 + (((size_t)max_det * 4 + 15) & ~(size_t)15);
-    b += kNmsChunk * 16 + kNmsChunk * 4 + kNmsChunk * 8 + 32;
+    b += 2 * kNmsChunk * 16 + 2 * kNmsChunk * 4 + kNmsChunk * 8 + kNmsChunk + 32;
     return b;
 }
 
@@ -249,14 +251,15 @@ __device__ __forceinline__ NmsSmem carve(unsigned char* base, int M, int MCp, in
     s.ccls = reinterpret_cast<unsigned short*>(base); base += (((size_t)M * 2 + 15) & ~(size_t)15);
     s.kbox = reinterpret_cast<float4*>(base); base += (size_t)max_det * 16;
     s.karea = reinterpret_cast<float*>(base); base += (((size_t)max_det * 4 + 15) & ~(size_t)15);
-    s.chbox = reinterpret_cast<float4*>(base); base += kNmsChunk * 16;
-    s.charea = reinterpret_cast<float*>(base); base += kNmsChunk * 4;
+    s.chbox = reinterpret_cast<float4*>(base); base += 2 * kNmsChunk * 16;
+    s.charea = reinterpret_cast<float*>(base); base += 2 * kNmsChunk * 4;
     s.cmask = reinterpret_cast<unsigned int*>(base); base += kNmsChunk * 8;
+    s.alist = reinterpret_cast<unsigned char*>(base); base += kNmsChunk;
     s.misc = reinterpret_cast<unsigned int*>(base);
     unsigned char* tail = reinterpret_cast<unsigned char*>(s.keys + M);
     s.kcn = reinterpret_cast<unsigned int*>(tail); tail += (size_t)max_det * 4;
     s.khead = reinterpret_cast<unsigned short*>(tail); tail += kNmsListClasses * 2;
-    s.chcls = reinterpret_cast<unsigned short*>(tail); tail += kNmsChunk * 2;
+    s.chcls = reinterpret_cast<unsigned short*>(tail); tail += 2 * kNmsChunk * 2;
     s.lists_fit = tail <= reinterpret_cast<unsigned char*>(s.keys + MCp) && (size_t)max_det * 16 >= kNmsListClasses * 4;
     s.chist = reinterpret_cast<unsigned int*>(s.kbox);
     return s;
@@ -325,6 +328,24 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& 
         return p.iou_tie_up ? lhs >= rhs : lhs > rhs;
     }
     return (double)__fdiv_rn(inter, u) > p.iou_thres;
+}
+
+// Branch-free front of iou_gt for the two suppression passes (ncu, round 2: the five early-outs of iou_gt serialised the four
+// "independent" tests of an unrolled trip: 35 issued instructions and 5 branch bubbles per test, 27 % of the kernel's stall
+// samples were `wait` behind those branches).  `res` is iou_gt's answer whenever `amb` is false: the fp32 estimate of mid*u is
+// off by at most 2^-23 relative, so outside a 1e-6 band around it the exact fp64 comparison cannot come out differently, and an
+// exactly empty intersection never exceeds a positive threshold; everything else (the band, zero / huge / NaN operands, a
+// non-positive threshold, for which the host sets iou_mid_f = NaN) is `amb` and goes through iou_gt itself.
+__device__ __forceinline__ void iou_fast(const float4& a, float aa, const float4& b, float ab, const NmsParams& p, bool& res, bool& amb) {
+    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float inter = __fmul_rn(w, h);
+    const float u = __fsub_rn(__fadd_rn(aa, ab), inter);
+    const float tq = __fmul_rn(p.iou_fast_mid, u);
+    const bool sane = (tq > 1.0e-30f) & (fmaxf(u, inter) < 3.0e38f);            // false for NaN operands too
+    const bool above = inter > __fmul_rn(tq, 1.000001f), below = inter < __fmul_rn(tq, 0.999999f);
+    res = above & sane;
+    amb = !(((above | below) & sane) | (inter == p.iou_zero));                    // iou_zero: 0, or NaN when the threshold is not positive
 }
 
 __device__ void bitonic_sort_desc(unsigned long long* keys, int n2) {
@@ -447,79 +468,64 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
     int* kidx = p.kept_idx ? p.kept_idx + (long long)n * p.max_det : nullptr;
     int nk = 0;
     const int t = threadIdx.x;
-    for (int c0 = 0; c0 < cnt && nk < p.max_det; c0 += kNmsChunk) {
-        const int cn = min(kNmsChunk, cnt - c0);
-        if (t < kNmsChunk) {
-            s.cmask[2 * t] = 0u; s.cmask[2 * t + 1] = 0u;
-            if (t < cn) {
-                const unsigned int slot = (unsigned int)(s.keys[c0 + t] & 0xFFFFull);
-                const float4 b = s.cbox[slot];
-                const float off = __fmul_rn((float)s.ccls[slot], p.max_wh);            // utils/utils.py:283
-                const float4 ob = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
-                s.chbox[t] = ob;
-                s.charea[t] = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
-                if (by_class) s.chcls[t] = s.ccls[slot];
-            }
+    // Chunk c of 64 sorted candidates is staged (offset boxes, areas, classes) into buffer c & 1 while chunk c - 1 is being resolved.
+    // Per chunk: (a) the chunk against everything kept so far -> dead bits; (b) pairs among the survivors -> kill rows; (c) greedy
+    // resolve over the rows + (d) append.  Round-2 profile of the first version of this loop (a 64x64 pair matrix on all threads with
+    // 16 branchy tests each, a one-thread resolve over 64-bit masks, separate load and append phases, five barriers), per image:
+    // pair matrix 37 us, resolve 26 us, load + append 7 us of 146 -- most rows of the matrix belonged to candidates (a) had already
+    // killed, and 255 threads waited on the resolve.  (Tried and dropped: resolving inside one warp with the IoU tests on the chain,
+    // one or four picks per trip: 185 / 209 us per launch against 203 before.)
+    auto stage = [&](int c0, int buf, int j) {               // candidate j of the chunk starting at sorted position c0
+        if (c0 + j < cnt) {
+            const unsigned int slot = (unsigned int)(s.keys[c0 + j] & 0xFFFFull);
+            const float4 b = s.cbox[slot];
+            const float off = __fmul_rn((float)s.ccls[slot], p.max_wh);            // utils/utils.py:283
+            const float4 ob = make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+            s.chbox[buf * kNmsChunk + j] = ob;
+            s.charea[buf * kNmsChunk + j] = __fmul_rn(__fsub_rn(ob.z, ob.x), __fsub_rn(ob.w, ob.y));
+            if (by_class) s.chcls[buf * kNmsChunk + j] = s.ccls[slot];
         }
-        if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }
-        __syncthreads();
-        tick(2);
+    };
+    if (t < kNmsChunk) stage(0, 0, t);
+    if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }
+    __syncthreads();
+    tick(2);
+    for (int c0 = 0, it = 0; c0 < cnt && nk < p.max_det; c0 += kNmsChunk, ++it) {
+        const int cn = min(kNmsChunk, cnt - c0);
+        const float4* chbox = s.chbox + (it & 1) * kNmsChunk;
+        const float* charea = s.charea + (it & 1) * kNmsChunk;
+        const unsigned short* chcls = s.chcls + (it & 1) * kNmsChunk;
         ++nchunks;
         {   // (a) chunk candidates against everything kept so far
             const int j = t & (kNmsChunk - 1), q = t / kNmsChunk;
             if (j < cn && by_class) {
                 // walk the kept boxes of this candidate's class; the candidate's four threads test every fourth node
-                const float4 bj = s.chbox[j];
-                const float aj = s.charea[j];
+                const float4 bj = chbox[j];
+                const float aj = charea[j];
                 bool dead = false;
                 int k = 0;
-                for (unsigned i = s.khead[s.chcls[j]]; i != 0xFFFFu && !dead; i = s.kcn[i] >> 16, ++k)
+                for (unsigned i = s.khead[chcls[j]]; i != 0xFFFFu && !dead; i = s.kcn[i] >> 16, ++k)
                     if ((k & (NT / kNmsChunk - 1)) == q) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
                 if (dead) atomicOr(&s.misc[1 + (j >> 5)], 1u << (j & 31));
-            } else if (p.variant == 1) {
-                // dense set, transposed: a warp owns 8 of the chunk's candidates and walks the kept boxes 32 at a time, lane = kept box
-                // (two conflict-free loads per block instead of two per test), candidate = broadcast load.  A candidate leaves the walk
-                // at the first block that suppresses it (warp vote), so the ~3/4 of a crowded chunk that die stop costing tests; the
-                // lane-per-candidate scan below only ends when its last surviving lane has seen every kept box.  Same tests, same result.
-                const int wp = t >> 5, ln = t & 31;
-                constexpr int CPW = kNmsChunk / (NT / 32);
-                unsigned alive = 0u;
-#pragma unroll
-                for (int jj = 0; jj < CPW; ++jj) if (wp * CPW + jj < cn) alive |= 1u << jj;
-                const unsigned mine = alive;
-                for (int kb = 0; kb < nk && alive; kb += 32) {
-                    const int i = kb + ln;
-                    const bool vi = i < nk;
-                    const float4 kx = s.kbox[vi ? i : 0];
-                    const float ka = s.karea[vi ? i : 0];
-                    unsigned m = alive;
-                    while (m) {
-                        const int j0 = __ffs((int)m) - 1;
-                        m &= m - 1u;
-                        const int j1 = m ? __ffs((int)m) - 1 : j0;       // second candidate of the trip (independent chain)
-                        m &= m - 1u;                                       // (0 & anything stays 0)
-                        const float4 b0 = s.chbox[wp * CPW + j0], b1 = s.chbox[wp * CPW + j1];
-                        const float a0 = s.charea[wp * CPW + j0], a1 = s.charea[wp * CPW + j1];
-                        const bool d0 = vi && iou_gt(kx, ka, b0, a0, p);
-                        const bool d1 = vi && iou_gt(kx, ka, b1, a1, p);
-                        if (__any_sync(0xffffffffu, d0)) alive &= ~(1u << j0);
-                        if (__any_sync(0xffffffffu, d1)) alive &= ~(1u << j1);
-                    }
-                }
-                const unsigned deadb = mine & ~alive;
-                if (ln == 0 && deadb) atomicOr(&s.misc[1 + (wp * CPW >> 5)], deadb << ((wp * CPW) & 31));
             } else if (j < cn) {
-                const float4 bj = s.chbox[j];
-                const float aj = s.charea[j];
+                const float4 bj = chbox[j];
+                const float aj = charea[j];
                 // four kept boxes per trip: the loads and IoU tests are independent, only the exit test is shared
                 bool dead = false;
                 constexpr int STEP = NT / kNmsChunk;
                 int i = q;
                 for (; i + 3 * STEP < nk && !dead; i += 4 * STEP) {
-                    const bool d0 = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
-                    const bool d1 = iou_gt(s.kbox[i + STEP], s.karea[i + STEP], bj, aj, p);
-                    const bool d2 = iou_gt(s.kbox[i + 2 * STEP], s.karea[i + 2 * STEP], bj, aj, p);
-                    const bool d3 = iou_gt(s.kbox[i + 3 * STEP], s.karea[i + 3 * STEP], bj, aj, p);
+                    bool d0, d1, d2, d3, m0, m1, m2, m3;
+                    iou_fast(s.kbox[i], s.karea[i], bj, aj, p, d0, m0);
+                    iou_fast(s.kbox[i + STEP], s.karea[i + STEP], bj, aj, p, d1, m1);
+                    iou_fast(s.kbox[i + 2 * STEP], s.karea[i + 2 * STEP], bj, aj, p, d2, m2);
+                    iou_fast(s.kbox[i + 3 * STEP], s.karea[i + 3 * STEP], bj, aj, p, d3, m3);
+                    if (m0 | m1 | m2 | m3) {                                   // rare: some pair sits in the 1e-6 band / is degenerate
+                        d0 = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
+                        d1 = iou_gt(s.kbox[i + STEP], s.karea[i + STEP], bj, aj, p);
+                        d2 = iou_gt(s.kbox[i + 2 * STEP], s.karea[i + 2 * STEP], bj, aj, p);
+                        d3 = iou_gt(s.kbox[i + 3 * STEP], s.karea[i + 3 * STEP], bj, aj, p);
+                    }
                     dead = d0 | d1 | d2 | d3;
                 }
                 for (; i < nk && !dead; i += STEP) dead = iou_gt(s.kbox[i], s.karea[i], bj, aj, p);
@@ -528,51 +534,68 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
         }
         __syncthreads();
         tick(3);
-        {   // (b) pairs inside the chunk: thread -> row i, 16 columns.  Candidates that (a) already found suppressed can neither keep
-            // nor be consulted in the resolve below, so their rows and columns are skipped (most of the chunk in a crowded class)
-            const unsigned long long deadm = ((unsigned long long)s.misc[2] << 32) | s.misc[1];
-            const int i = t >> 2, jq = t & 3;
-            if (i < cn && !((deadm >> i) & 1ull)) {
-                const float4 bi = s.chbox[i];
-                const float ai = s.charea[i];
-                const unsigned short ci = by_class ? s.chcls[i] : (unsigned short)0;
-                unsigned int bits = 0u;
-#pragma unroll 4
-                for (int e = 0; e < 16; ++e) {
-                    const int j = jq * 16 + e;
-                    if (j > i && j < cn && !((deadm >> j) & 1ull) && (!by_class || s.chcls[j] == ci) && iou_gt(bi, ai, s.chbox[j], s.charea[j], p))
-                        bits |= 1u << e;
+        // (b) pairs INSIDE the chunk, only among the candidates (a) left alive (typically ~20 of 64 in a crowded class): the live
+        // candidates are ranked (alist), thread <-> ordered pair of ranks, one IoU test per thread and round, hits OR-ed into the
+        // 64-bit kill row of the earlier candidate.  Threads 64..127 meanwhile stage the next chunk into the other buffer.
+        unsigned long long alive = ~(((unsigned long long)s.misc[2] << 32) | s.misc[1]);
+        if (cn < 64) alive &= (1ull << cn) - 1ull;
+        const int na = __popcll(alive);
+        if (t < kNmsChunk) {
+            s.cmask[2 * t] = 0u; s.cmask[2 * t + 1] = 0u;
+            if ((alive >> t) & 1ull) s.alist[__popcll(alive & ((1ull << t) - 1ull))] = (unsigned char)t;
+        } else if (t < 2 * kNmsChunk) {
+            stage(c0 + kNmsChunk, (it + 1) & 1, t - kNmsChunk);       // (nothing to do past the end)
+        }
+        __syncthreads();
+        if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }              // every thread has read the dead bits
+        for (int pi = t; pi < na * na; pi += NT) {
+            const int rx = pi / na, ry = pi - rx * na;
+            if (ry > rx) {
+                const int x = s.alist[rx], y = s.alist[ry];           // x earlier (higher confidence) than y
+                if (!by_class || chcls[x] == chcls[y]) {
+                    bool d, m;
+                    iou_fast(chbox[x], charea[x], chbox[y], charea[y], p, d, m);
+                    if (m) d = iou_gt(chbox[x], charea[x], chbox[y], charea[y], p);
+                    if (d) atomicOr(&s.cmask[2 * x + (y >> 5)], 1u << (y & 31));
                 }
-                if (bits) atomicOr(&s.cmask[2 * i + (jq >> 1)], bits << ((jq & 1) * 16));
             }
         }
         __syncthreads();
         tick(4);
-        if (t == 0) {   // (c) serial resolve
-            unsigned long long alive = ~(((unsigned long long)s.misc[2] << 32) | s.misc[1]);
-            if (cn < 64) alive &= (1ull << cn) - 1ull;
-            unsigned long long kept = 0ull;
+        // (c) greedy resolve over the kill rows, run redundantly by every thread (no hand-off barrier): the lowest live candidate is
+        // kept and its row cleared from the live set.  Two 32-bit halves keep the dependent chain short (find-first-set, one shared
+        // load, one logic op per kept candidate); a row's upper half is applied to the upper live bits off the chain.
+        unsigned long long kept;
+        {
+            unsigned int lo = (unsigned int)alive, hi = (unsigned int)(alive >> 32), klo = 0u, khi = 0u;
             int room = p.max_det - nk;
-            int pos = nk;
-            while (alive && room > 0) {
-                const int i = __ffsll((long long)alive) - 1;
-                kept |= 1ull << i;
+            while (lo && room > 0) {
+                const int i = __ffs((int)lo) - 1;
+                klo |= 1u << i;
                 --room;
-                if (by_class) { const unsigned c = s.chcls[i]; s.kcn[pos] = c | ((unsigned)s.khead[c] << 16); s.khead[c] = (unsigned short)pos; }
-                ++pos;
-                const unsigned long long m = ((unsigned long long)s.cmask[2 * i + 1] << 32) | s.cmask[2 * i];
-                alive &= ~m;
-                alive &= ~(1ull << i);
+                lo &= ~(1u << i) & ~s.cmask[2 * i];
+                hi &= ~s.cmask[2 * i + 1];
             }
-            s.misc[3] = (unsigned int)kept; s.misc[4] = (unsigned int)(kept >> 32);
+            while (hi && room > 0) {
+                const int i = __ffs((int)hi) - 1;
+                khi |= 1u << i;
+                --room;
+                hi &= ~(1u << i) & ~s.cmask[2 * (i + 32) + 1];
+            }
+            kept = ((unsigned long long)khi << 32) | (unsigned long long)klo;
         }
-        __syncthreads();
-        tick(5);
-        const unsigned long long kept = ((unsigned long long)s.misc[4] << 32) | s.misc[3];
+        if (by_class && t == 0) {                                     // per-class lists of kept boxes, in kept order
+            int pos = nk;
+            for (unsigned long long r = kept; r; r &= r - 1ull, ++pos) {
+                const unsigned c = chcls[__ffsll((long long)r) - 1];
+                s.kcn[pos] = c | ((unsigned)s.khead[c] << 16);
+                s.khead[c] = (unsigned short)pos;
+            }
+        }
         if (t < cn && ((kept >> t) & 1ull)) {   // (d) append
             const int pos = nk + __popcll(kept & ((1ull << t) - 1ull));
-            s.kbox[pos] = s.chbox[t];
-            s.karea[pos] = s.charea[t];
+            s.kbox[pos] = chbox[t];
+            s.karea[pos] = charea[t];
             const unsigned long long key = s.keys[c0 + t];
             const unsigned int slot = (unsigned int)(key & 0xFFFFull);
             const float4 b = s.cbox[slot];
@@ -584,7 +607,7 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
         }
         nk += __popcll(kept);
         __syncthreads();
-        tick(6);
+        tick(5);
     }
     if (t == 0) p.counts[n] = nk;
     for (int i = nk * 6 + t; i < p.max_det * 6; i += NT) out[i] = 0.f;
@@ -710,62 +733,160 @@ __device__ __forceinline__ void thread_cell_candidates(const PostGeom& g, const 
     }
 }
 
-template <bool PROF>
+// The common shape (80 classes, 3 anchors) with everything static.  ncu on the generic version above (round 2, batch 256): the
+// candidate phase was 26 % of the kernel (59 us of 227 per image) and 5500 issued instructions per thread and pass, 70 % of them
+// predicated 64-bit address arithmetic for `(c < C) ? __ldg(cp + (long long)c * hw)`, with seven dependent global round trips per
+// pass (classes, then objectness and box logits anchor by anchor).  Here the class count is a constant, offsets are 32-bit, the
+// three objectness logits travel with the class logits and the box logits of all wanted anchors in one more batch, and the
+// near-tie count (which only depends on the cell) is taken once.  Same arithmetic, same results bit for bit.
+__device__ __forceinline__ void thread_cell_candidates_80x3(const PostGeom& g, const NmsParams& p, const NmsSmem& s, int n, int lv, int cell,
+                                                            bool in_range, int row0) {
+    constexpr int A = 3, C = kCT;
+    const int hw = g.hw[lv];
+    float e[C];
+    float sum = 1.f, emax = 0.f;
+    int cstar = 0, nnear = 0;
+    float ol[A] = {0.f, 0.f, 0.f};
+    if (in_range) {
+        const float* cp = g.cls[lv] + (long long)n * C * hw + cell;
+        const float* op = g.obj[lv] + (long long)n * A * hw + cell;
+#pragma unroll
+        for (int c = 0; c < C; ++c) e[c] = __ldg(cp + c * hw);
+#pragma unroll
+        for (int a = 0; a < A; ++a) ol[a] = __ldg(op + a * hw);
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < C; ++c) m = fmaxf(m, e[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            e[c] = expf(__fsub_rn(e[c], m));
+            if (e[c] > emax) { emax = e[c]; cstar = c; }             // first arg-max
+        }
+        float ps[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            float t = e[l];                                           // (0 + e_l) is exact
+            if (l + 32 < C) t = __fadd_rn(t, e[l + 32]);
+            if (l + 64 < C) t = __fadd_rn(t, e[l + 64]);
+            ps[l] = t;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < o; ++i) ps[i] = __fadd_rn(ps[i], ps[i + o]);
+        sum = ps[0];
+        const float near = emax * 0.99999f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) nnear += (e[c] >= near) ? 1 : 0;
+    }
+    bool want[A];
+    float conf[A];
+    int cls[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        want[a] = false; conf[a] = 0.f; cls[a] = cstar;
+        if (in_range) {
+            const float obj = sigmoid_rn(ol[a]);
+            if (obj > p.conf_thres) {
+                conf[a] = __fmul_rn(__fdiv_rn(emax, sum), obj);
+                if (nnear > 1) {                                      // rare: an earlier class may round to the same product
+                    const float near = emax * 0.99999f;
+                    bool found = false;
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (!found && c < cstar && e[c] >= near && __fmul_rn(__fdiv_rn(e[c], sum), obj) == conf[a]) { cls[a] = c; found = true; }
+                }
+                want[a] = conf[a] > p.conf_thres && class_ok(p, cls[a]);
+            }
+        }
+    }
+    const int y = cell / g.w[lv], x = cell - y * g.w[lv];
+    float r[A][4];
+    {
+        const float* rp = g.reg[lv] + (long long)n * 4 * A * hw + cell;
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[a][k] = want[a] ? __ldg(rp + (4 * a + k) * hw) : 0.f;
+    }
+    const float st = g.stride[lv];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        float bx = 0.f, by = 0.f, bw = 0.f, bh = 0.f;
+        if (want[a]) {
+            const float sx = sigmoid_rn(r[a][0]), sy = sigmoid_rn(r[a][1]), sw = sigmoid_rn(r[a][2]), sh = sigmoid_rn(r[a][3]);
+            bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), (float)x), st);
+            by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), (float)y), st);
+            const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+            bw = (float)__dmul_rn((double)__fmul_rn(tw, tw), g.anc[lv][a][0]);
+            bh = (float)__dmul_rn((double)__fmul_rn(th, th), g.anc[lv][a][1]);
+        }
+        const unsigned int slot = alloc_slots(s, want[a]);
+        if (want[a]) write_candidate(s, slot, bx, by, bw, bh, conf[a], cls[a], row0 + cell * A + a, p.max_wh);
+    }
+}
+
+// FAST selects the candidate generation at compile time (one path per kernel: the register allocation and the instruction footprint
+// of one path no longer pay for the others): 2 = thread per cell with 80 classes x 3 anchors static, 1 = thread per cell, generic
+// (C <= 80), 0 = warp per cell (any C).
+template <bool PROF, int FAST>
 __global__ void __launch_bounds__(NT, 2)
-decode_nms_kernel(PostGeom g, NmsParams p, int fast) {
+decode_nms_kernel(PostGeom g, NmsParams p) {
     pdl_wait();
     const long long tstart = PROF ? clock64() : 0ll;
     extern __shared__ __align__(16) unsigned char smraw[];
     const NmsSmem s = carve(smraw, p.M, p.MCp, p.max_det);
-    float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
     const int n = blockIdx.x;
     if (threadIdx.x == 0) { s.misc[0] = 0u; s.misc[5] = 0u; }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A = g.A, C = g.C;
-    if (fast) {
+    if (FAST) {
         __syncthreads();
+#pragma unroll 1
         for (int lv = 0; lv < 2; ++lv) {
             const int row0 = lv ? g.hw[0] * A : 0;
+#pragma unroll 1
             for (int c0 = 0; c0 < g.hw[lv]; c0 += NT) {
                 const int cell = c0 + threadIdx.x;
                 const bool in_range = cell < g.hw[lv];
-                thread_cell_candidates(g, p, s, n, lv, in_range ? cell : 0, in_range, row0);
+                if (FAST == 2) thread_cell_candidates_80x3(g, p, s, n, lv, in_range ? cell : 0, in_range, row0);
+                else thread_cell_candidates(g, p, s, n, lv, in_range ? cell : 0, in_range, row0);
             }
         }
-        sort_and_suppress<PROF>(s, p, n, tstart);
-        return;
-    }
-    for (int lv = 0; lv < 2; ++lv) {
-        const int row0 = lv ? g.hw[0] * A : 0;
-        for (int cell0 = 0; cell0 < g.hw[lv]; cell0 += kChunkCells) {
-            const int ncell = min(kChunkCells, g.hw[lv] - cell0);
-            __syncthreads();
-            stage_cells(S, g, n, lv, cell0, ncell);
-            __syncthreads();
-            for (int cl = warp; cl < ncell; cl += NT / 32) {
-                CellRegs r;
-                decode_cell(S, g, lv, cell0 + cl, cl, lane, r);
-                float my_conf = 0.f;
-                int my_cls = 0;
-                bool my_want = false;
-                for (int a = 0; a < A; ++a) {
-                    const float obj = __shfl_sync(0xffffffffu, r.ob, a);
-                    if (!(obj > p.conf_thres)) continue;
-                    float best = -INFINITY;
-                    int bi = 0x7fffffff;
+    } else {
+        float* S = reinterpret_cast<float*>(smraw + nms_smem_bytes(p.M, p.MCp, p.max_det));
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int lv = 0; lv < 2; ++lv) {
+            const int row0 = lv ? g.hw[0] * A : 0;
+            for (int cell0 = 0; cell0 < g.hw[lv]; cell0 += kChunkCells) {
+                const int ncell = min(kChunkCells, g.hw[lv] - cell0);
+                __syncthreads();
+                stage_cells(S, g, n, lv, cell0, ncell);
+                __syncthreads();
+                for (int cl = warp; cl < ncell; cl += NT / 32) {
+                    CellRegs r;
+                    decode_cell(S, g, lv, cell0 + cl, cl, lane, r);
+                    float my_conf = 0.f;
+                    int my_cls = 0;
+                    bool my_want = false;
+                    for (int a = 0; a < A; ++a) {
+                        const float obj = __shfl_sync(0xffffffffu, r.ob, a);
+                        if (!(obj > p.conf_thres)) continue;
+                        float best = -INFINITY;
+                        int bi = 0x7fffffff;
 #pragma unroll
-                    for (int j = 0; j < kCPL; ++j) {
-                        const int c = lane + 32 * j;
-                        if (c < C) {
-                            const float v = __fmul_rn(r.p[j], obj);
-                            if (v > best) { best = v; bi = c; }
+                        for (int j = 0; j < kCPL; ++j) {
+                            const int c = lane + 32 * j;
+                            if (c < C) {
+                                const float v = __fmul_rn(r.p[j], obj);
+                                if (v > best) { best = v; bi = c; }
+                            }
                         }
+                        warp_argmax(best, bi);
+                        if (lane == a && best > p.conf_thres && class_ok(p, bi)) { my_want = true; my_conf = best; my_cls = bi; }
                     }
-                    warp_argmax(best, bi);
-                    if (lane == a && best > p.conf_thres && class_ok(p, bi)) { my_want = true; my_conf = best; my_cls = bi; }
+                    const unsigned int slot = alloc_slots(s, my_want);
+                    if (my_want) write_candidate(s, slot, r.bx, r.by, r.bw, r.bh, my_conf, my_cls, row0 + (cell0 + cl) * A + lane, p.max_wh);
                 }
-                const unsigned int slot = alloc_slots(s, my_want);
-                if (my_want) write_candidate(s, slot, r.bx, r.by, r.bw, r.bh, my_conf, my_cls, row0 + (cell0 + cl) * A + lane, p.max_wh);
             }
         }
     }
@@ -807,6 +928,8 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
         const float f1 = nextafterf(f0, INFINITY);          // smallest float > thr
         p.iou_mid = ((double)f0 + (double)f1) * 0.5;
         p.iou_mid_f = (float)p.iou_mid;
+        p.iou_fast_mid = p.iou_mid > 0.0 ? p.iou_mid_f : nanf("");
+        p.iou_zero = p.iou_mid > 0.0 ? 0.f : nanf("");
         unsigned int bits; memcpy(&bits, &f1, 4);
         p.iou_tie_up = (bits & 1u) == 0u;                   // ties-to-even: the midpoint rounds to f1 iff f1 is even
     }
@@ -816,8 +939,6 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
     while (p.MCp < M) p.MCp <<= 1;
     p.C = 1 << 30;                                           // callers that know the class count set it
     p.prof = nullptr;
-    static const int variant = getenv("YFV2_NMS_V") ? atoi(getenv("YFV2_NMS_V")) : 0;
-    p.variant = variant;
     return YFV2_OK;
 }
 }  // namespace
@@ -884,10 +1005,16 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
     rc = fill_nms(p, g.M, conf_thres, iou_thres, class_filter, n_filter, max_det, max_wh, out, counts, kept_idx);
     if (rc) return rc;
     p.C = C;
-    const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (size_t)(5 * A + C) * kSStride * sizeof(float);
-    if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
     p.prof = g_nms_prof;
-    auto kern = p.prof ? decode_nms_kernel<true> : decode_nms_kernel<false>;
+    // 2: thread per cell, 80 classes x 3 anchors all static; 1: thread per cell, generic (C <= 80); 0: warp per cell
+    static const bool warp_cells = getenv("YFV2_NMS_WARP_PER_CELL") != nullptr, generic_cells = getenv("YFV2_NMS_GENERIC_CELLS") != nullptr;
+    const int fast = (C > kCT || warp_cells) ? 0 : (C == kCT && A == 3 && !generic_cells) ? 2 : 1;
+    void (*kern)(PostGeom, NmsParams) =
+        p.prof ? (fast == 2 ? decode_nms_kernel<true, 2> : fast == 1 ? decode_nms_kernel<true, 1> : decode_nms_kernel<true, 0>)
+               : (fast == 2 ? decode_nms_kernel<false, 2> : fast == 1 ? decode_nms_kernel<false, 1> : decode_nms_kernel<false, 0>);
+    // the warp-per-cell path stages 5A+C logits of 32 cells behind the NMS state
+    const size_t bytes = nms_smem_bytes(p.M, p.MCp, p.max_det) + (fast ? 0 : (size_t)(5 * A + C) * kSStride * sizeof(float));
+    if (bytes > kSmemCap) { set_error("decode_nms: %zu bytes of shared memory needed", bytes); return YFV2_EUNSUPPORTED; }
     YFV2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     {   // nothing is read before pdl_wait(), so overlapping the predecessor's tail is always safe
         cudaLaunchConfig_t cfg{};
@@ -896,8 +1023,7 @@ extern "C" int yfv2_decode_nms(const float* const preds[6], int N, int H, int W,
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = pdl_allowed() ? 1 : 0;
-        const int fast = (C <= kCT && !getenv("YFV2_NMS_WARP_PER_CELL")) ? 1 : 0;
-        YFV2_CUDA(cudaLaunchKernelEx(&cfg, kern, g, p, fast));
+        YFV2_CUDA(cudaLaunchKernelEx(&cfg, kern, g, p));
     }
     YFV2_LAUNCH_CHECK();
     return YFV2_OK;
