@@ -633,13 +633,17 @@ struct Pw3Args {
     int N, nout;
 };
 
-template <int KA, int KB, int SHA, int NP, int G, bool RELU, int KC = 16>
-__global__ void __launch_bounds__(G * 128, 1)
+// SIB = 2: sibling warps as in s1c_kernel.  TMEM (G column blocks of NB*2*KC + NP) caps the kernel at three warpgroups = 12 warps
+// per SM, and ncu (profiles/r2_final_kernels_ncu.txt) shows them waiting on their global loads (long scoreboard 2.4-3.1 per issue,
+// issue slots 36-38 % busy).  Warps w and w + 4 of a group share a lane quarter: each loads, splits and stores half of a chunk's
+// channels, the last of the EIGHT warps issues the chunk's MMAs, and each drains half of the accumulator columns.
+template <int KA, int KB, int SHA, int NP, int G, bool RELU, int KC = 16, int SIB = 1>
+__global__ void __launch_bounds__(G * 128 * SIB, 1)
 pw3_kernel(const __grid_constant__ Pw3Args p) {
     pdl_trigger();
-    constexpr int KP = KA + KB, NB = 2, NCH = KP / KC;
+    constexpr int KP = KA + KB, NB = 2, NCH = KP / KC, KCS = KC / SIB;
     constexpr int COLS = NB * 2 * KC + NP;
-    static_assert(G * COLS <= 512 && KP % (2 * KC) == 0 && KA % KC == 0 && NP % 16 == 0 && KP <= kPwMaxK, "shape");
+    static_assert(G * COLS <= 512 && KP % (2 * KC) == 0 && KA % KC == 0 && NP % 16 == 0 && KP <= kPwMaxK && KCS % 8 == 0 && (SIB == 1 || SIB == 2), "shape");
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) BPipe pipes[G];
     __shared__ __align__(8) uint64_t wbar;
@@ -665,7 +669,9 @@ pw3_kernel(const __grid_constant__ Pw3Args p) {
     __syncthreads();
     fence_after_sync();
     BGrp g;
-    const int grp = threadIdx.x >> 7;
+    const int grp = threadIdx.x / (128 * SIB);
+    const int sub = SIB == 1 ? 0 : (warp >> 2) & 1;        // sibling index; the lane quarter is warp & 3 either way
+    const int koff = sub * KCS;
     g.tcol = tmem_slot + grp * COLS;
     g.tlane = g.tcol + ((uint32_t)(32 * (warp & 3)) << 16);
     g.pipe = &pipes[grp];
@@ -676,6 +682,9 @@ pw3_kernel(const __grid_constant__ Pw3Args p) {
     const int HW = p.out.H * p.out.W, W = p.out.W;
     const long long total = (long long)p.N * HW;
     const int ntiles = (int)((total + 127) / 128);
+    // accumulator columns this warp drains: everything, or the sibling's half (in blocks of 16)
+    constexpr int NBLK = NP / 16, H0 = (NBLK + 1) / 2;
+    const int n_lo = SIB == 1 ? 0 : (sub ? H0 * 16 : 0), n_hi = SIB == 1 ? NP : (sub ? NP : H0 * 16);
     pdl_wait();                                            // predecessor's activations are complete and visible from here on
     mbar_wait(&wbar, 0);
     for (int tile = blockIdx.x * G + grp; tile < ntiles; tile += gridDim.x * G) {
@@ -687,28 +696,71 @@ pw3_kernel(const __grid_constant__ Pw3Args p) {
         const int y = px / W, x = px - y * W;
         const float* baseA = p.A.base + (long long)n * p.A.sN + p.A.org + (y >> SHA) * p.A.Ws + (x >> SHA);
         const float* baseB = p.B.base + (long long)n * p.B.sN + p.B.org + y * p.B.Ws + x;
-        float v[2][KC];
+        float v[2][KCS];
         auto load = [&](int c, float* dst) {               // c is a multiple-of-KC chunk index; chunks never straddle the A / B split
             const float* base = (c * KC < KA) ? baseA : baseB;
 #pragma unroll
-            for (int j = 0; j < KC; ++j) dst[j] = __ldcg(base + p.in_off[c * KC + j]);
+            for (int j = 0; j < KCS; ++j) dst[j] = __ldcg(base + p.in_off[c * KC + koff + j]);
+        };
+        auto store = [&](const float* a) {                  // this warp's KCS channels of the chunk -> hi / lo columns of the current A buffer
+            const uint32_t col = g.tlane + (g.chunk % NB) * (2 * KC) + koff;
+#pragma unroll
+            for (int j = 0; j < KCS; j += 8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    hi[i] = __float_as_uint(a[j + i]) & 0xFFFFE000u;
+                    lo[i] = __float_as_uint(a[j + i] - __uint_as_float(hi[i]));
+                }
+                tmem_st8(col + j, hi);
+                tmem_st8(col + KC + j, lo);
+            }
+        };
+        auto hand_off = [&](int c, bool last) {            // st_hand_off with 4 * SIB arriving warps
+            wait_st();
+            fence_before_sync();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                const uint32_t buf = g.chunk % NB;
+                const uint32_t old = atom_inc_acq_rel(&g.pipe->arrivals[buf]);
+                if ((old & (4u * SIB - 1u)) == 4u * SIB - 1u) {
+                    fence_after_sync();
+                    constexpr uint32_t idesc = make_idesc_tf32(128, NP);
+                    constexpr uint32_t LBO = 128, SBO = (KP / 4) * 128;
+                    const uint32_t a_hi = g.tcol + buf * (2 * KC), a_lo = a_hi + KC, d = g.tcol + NB * 2 * KC;
+#pragma unroll
+                    for (int s2 = 0; s2 < KC / 8; ++s2) {
+                        const int ks = c * (KC / 8) + s2;
+                        const uint64_t bh = make_b_desc(b_hi + ks * 256, LBO, SBO);
+                        const uint64_t bl = make_b_desc(b_lo + ks * 256, LBO, SBO);
+                        mma_tf32_ts(d, a_lo + 8 * s2, bh, idesc, ks > 0 ? 1u : 0u);      // small terms first
+                        mma_tf32_ts(d, a_hi + 8 * s2, bl, idesc, 1u);
+                        mma_tf32_ts(d, a_hi + 8 * s2, bh, idesc, 1u);
+                    }
+                    mma_commit(&g.pipe->empty[buf]);
+                    if (last) mma_commit(&g.pipe->dfull);
+                }
+            }
+            __syncwarp();
+            ++g.chunk;
         };
         load(0, v[0]);
 #pragma unroll 1
         for (int c = 0; c < NCH; c += 2) {
             load(c + 1, v[1]);
             st_acquire<NB>(g);
-            st_store<KC, NB>(g, v[0]);
-            st_hand_off<KP, NP, KC, NB>(g, c, b_hi, b_lo, NB * 2 * KC, false);
+            store(v[0]);
+            hand_off(c, false);
             if (c + 2 < NCH) load(c + 2, v[0]);
             st_acquire<NB>(g);
-            st_store<KC, NB>(g, v[1]);
-            st_hand_off<KP, NP, KC, NB>(g, c + 1, b_hi, b_lo, NB * 2 * KC, c + 2 == NCH);
+            store(v[1]);
+            hand_off(c + 1, c + 2 == NCH);
         }
         st_wait_d(g);
         float* obase = p.out.base + (long long)n * p.out.sN + p.out.org + y * p.out.Ws + x;
 #pragma unroll
         for (int n0 = 0; n0 < NP; n0 += 16) {
+            if (n0 < n_lo || n0 >= n_hi) continue;
             float d[16];
             tmem_ld16v(g.tlane + NB * 2 * KC + n0, d);
             wait_ld();
@@ -835,17 +887,29 @@ int blk_launch_pw(int kind, const Planes& A, const ChanTab& ta, const Planes& B,
     a.A = A; a.B = B; a.out = out; a.wpack = wpack; a.N = N;
     const long long total = (long long)N * out.H * out.W;
     const int ntiles = (int)((total + 127) / 128);
-    auto run = [&](auto kern, int KA, int KB, int NP, int G, int nout) -> int {
+    auto run = [&](auto kern, int KA, int KB, int NP, int G, int nout, int sib = 1) -> int {
         a.nout = nout;
         for (int k = 0; k < KA; ++k) a.in_off[k] = (uint32_t)((long long)ta.c[k] * A.sC);
         for (int k = 0; k < KB; ++k) a.in_off[KA + k] = (uint32_t)((long long)tb.c[k] * B.sC);
         for (int k = 0; k < nout; ++k) a.out_off[k] = (uint32_t)((long long)tout.c[k] * out.sC);
         const size_t bytes = (size_t)(2 * NP * (KA + KB) + 2 * NP) * sizeof(float);
         TRYB(blk_smem_attr(kern, bytes));
-        YFV2_CUDA(launch_k(kern, min((ntiles + G - 1) / G, sm_count()), G * 128, bytes, s, pdl_take(), a));
+        YFV2_CUDA(launch_k(kern, min((ntiles + G - 1) / G, sm_count()), G * 128 * sib, bytes, s, pdl_take(), a));
         YFV2_LAUNCH_CHECK();
         return YFV2_OK;
     };
+    // sibling warps on three warpgroups (24 warps, 76-79 registers) by default: stage4.0 109.9 -> 105.9 us, fpn.S3 26.8 -> 25.2,
+    // fpn.S2 73.8 -> 69.7 at batch 256.  YFV2_PW_SIB=0: none (12 warps), 2: siblings on two warpgroups (16 warps; fpn.S2 78.5 us)
+    static const int pw_sib = getenv("YFV2_PW_SIB") ? atoi(getenv("YFV2_PW_SIB")) : 1;
+    if (pw_sib == 1) {
+        if (kind == 0) return run(pw3_kernel<96, 0, 0, 96, 3, true, 16, 2>, 96, 0, 96, 3, 96, 2);
+        if (kind == 1) return run(pw3_kernel<192, 0, 0, 80, 3, true, 16, 2>, 192, 0, 80, 3, 72, 2);
+        if (kind == 2) return run(pw3_kernel<192, 96, 1, 80, 3, true, 16, 2>, 192, 96, 80, 3, 72, 2);
+    } else if (pw_sib == 2) {
+        if (kind == 0) return run(pw3_kernel<96, 0, 0, 96, 2, true, 16, 2>, 96, 0, 96, 2, 96, 2);
+        if (kind == 1) return run(pw3_kernel<192, 0, 0, 80, 2, true, 16, 2>, 192, 0, 80, 2, 72, 2);
+        if (kind == 2) return run(pw3_kernel<192, 96, 1, 80, 2, true, 16, 2>, 192, 96, 80, 2, 72, 2);
+    }
     if (kind == 0) return run(pw3_kernel<96, 0, 0, 96, 3, true>, 96, 0, 96, 3, 96);
     if (kind == 1) return run(pw3_kernel<192, 0, 0, 80, 3, true>, 192, 0, 80, 3, 72);
     if (kind == 2) return run(pw3_kernel<192, 96, 1, 80, 3, true>, 192, 96, 80, 3, 72);

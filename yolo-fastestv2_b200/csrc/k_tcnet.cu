@@ -591,8 +591,39 @@ struct Dws2Args {
     const float* wdw[2];
     const float* wpw[2];
     int N, imgs, nbranch, nout;
+    int pair_rows;             // 1: window rows as LDS.64 + shuffle (frames of odd width: every window starts on an even float)
 };
 constexpr int kDwsBufs = 3;
+
+// Stride-2 rows without the 2-way bank conflict of scalar loads (consecutive lanes sit two floats apart and the frame pitch puts
+// every lane on an even bank: ncu on tc_dws2c_kernel<96,96,4>: 4.8 MIO-throttle stalls per issue, 4.7 M conflict wavefronts): the
+// first two taps of a window row come as ONE 8-byte load and the third is the right neighbour's first tap (one shuffle); lanes
+// whose right neighbour is another row / image / warp (`nb_ok` false) load it.  Every lane of the warp must call this (shuffles);
+// lanes without a pixel pass the window of pixel 0 and `valid` = false.  Same arithmetic and association as dw3n: bit-identical.
+template <int NC>
+__device__ __forceinline__ void dw3n_s2(const float* __restrict__ xk, int RS, int WS, const float* __restrict__ wk, bool valid, bool nb_ok, float* a) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const float4 wa = *reinterpret_cast<const float4*>(wk);
+        const float4 wb = *reinterpret_cast<const float4*>(wk + 4);
+        const float4 wc = *reinterpret_cast<const float4*>(wk + 8);
+        float2 v[3];
+        float c2[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            v[r] = *reinterpret_cast<const float2*>(xk + r * WS);
+            c2[r] = __shfl_down_sync(0xffffffffu, v[r].x, 1);
+            if (!nb_ok) c2[r] = xk[r * WS + 2];
+        }
+        float p0 = wa.x * v[0].x; p0 = fmaf(wa.y, v[0].y, p0); p0 = fmaf(wa.z, c2[0], p0);
+        float p1 = wa.w * v[1].x; p1 = fmaf(wb.x, v[1].y, p1); p1 = fmaf(wb.y, c2[1], p1);
+        float p2 = wb.z * v[2].x; p2 = fmaf(wb.w, v[2].y, p2); p2 = fmaf(wc.x, c2[2], p2);
+        const float d = (p0 + p1) + p2;
+        a[j] = valid ? fmaf(d, wc.y, wc.z) : 0.f;
+        xk += RS;
+        wk += 12;
+    }
+}
 
 // depthwise 3x3 + BN of NC consecutive channels of one output pixel (window top-left xk in the first plane, plane stride RS)
 template <int NC>
@@ -693,6 +724,7 @@ tc_dws2c_kernel(const __grid_constant__ Dws2Args p) {
             const int qi = valid ? q - im * HWo : 0;
             const int oy = qi / Wout, ox = qi - oy * Wout;
             const int woff = im * PS + (2 * oy + pad - 1) * WS + 2 * ox + pad - 1;      // window's top-left in the framed plane
+            const bool nb_ok = valid && ox + 1 < Wout && lane != 31;                    // the next lane holds the pixel to the right
             RowSink<true, false, false> sink;
             sink.scale = scale; sink.shift = shift; sink.valid = valid;
             sink.obase = p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox;
@@ -704,7 +736,8 @@ tc_dws2c_kernel(const __grid_constant__ Dws2Args p) {
                 for (int h = 0; h < 2; ++h, ++it) {
                     const uint32_t buf = it % NB;
                     mbar_wait(&fullb[buf], (it / NB) & 1u);
-                    dw3n<4>(X + (size_t)buf * SLOT + woff, CS, WS, sDW + (c * 8 + 4 * h) * DWR, valid, a + 4 * h);
+                    if (p.pair_rows) dw3n_s2<4>(X + (size_t)buf * SLOT + woff, CS, WS, sDW + (c * 8 + 4 * h) * DWR, valid, nb_ok, a + 4 * h);
+                    else dw3n<4>(X + (size_t)buf * SLOT + woff, CS, WS, sDW + (c * 8 + 4 * h) * DWR, valid, a + 4 * h);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&freeb[buf]);
                 }
@@ -1713,6 +1746,8 @@ int tc_launch_dws2c(int K, int nbranch, const Planes* in, const ChanTab* tin, co
     int G = 0; size_t bytes = 0;
     if (!tc_dws2c_supported(K, in[0], out[0], N, &a.imgs, &G, &bytes)) { set_error("tc_launch_dws2c: unsupported geometry"); return YFV2_EUNSUPPORTED; }
     const int items = nbranch * ((N + a.imgs - 1) / a.imgs);
+    static const bool scalar_rows = getenv("YFV2_DWS2_SCALAR") != nullptr;          // A/B: three scalar loads per window row
+    a.pair_rows = (!scalar_rows && (in[0].pad & 1) && (nbranch < 2 || (in[1].pad & 1))) ? 1 : 0;
     auto run = [&](auto kern, int g) -> int {
         TRYL(set_smem_attr(kern, bytes));
         YFV2_CUDA(launch_k(kern, min(items, sm_count()), g * 128 + 32, bytes, s, pdl_take(), a));
@@ -1799,7 +1834,10 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
     // ---- fast path: channel-streamed whole-image items ----------------------------------------------------------
     static const bool force_g4 = getenv("YFV2_HEADS_G4") != nullptr;
     // pairs pay off when every pair is full (even W); odd maps (11x11) keep one pixel per thread
-    if (W % 2 == 0 && H * (W / 2) <= 256 && !force_band && !force_g4) {
+    // odd maps (11x11 at 352x352) keep one pixel per thread: the pair kernel works on them (YFV2_HEADS_ODD_PAIRS=1, parity green) but
+    // its half-empty last pairs cost what the shared window rows save (measured: heads3.a 62.8 vs 59.5 us, heads3.b 60.9 vs 62.0 us)
+    static const bool odd_pairs = getenv("YFV2_HEADS_ODD_PAIRS") != nullptr;
+    if ((W % 2 == 0 || odd_pairs) && H * ((W + 1) / 2) <= 256 && !force_band && !force_g4) {
         // pixel pairs: 2 warpgroups x 2 tiles
         HeadArgs a{};
         a.N = N; a.nout = 72;
