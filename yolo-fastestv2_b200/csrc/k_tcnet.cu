@@ -471,6 +471,7 @@ struct HeadArgs {
     // two framed rows whose bank ranges overlap; ncu: 9.2 M conflict wavefronts per launch); build_lanemap() deals the pairs so that
     // the 16 lanes of a half-warp sit in 16 different 8-byte banks.
     int use_map;
+    int st2_ok;                // tc_head2w_kernel: a pixel pair may leave as one 8-byte store (even W, 8-byte aligned destinations)
     unsigned int lanemap[256];
 };
 constexpr int kHeadBufs = 4;
@@ -1171,16 +1172,12 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
             const int oy = r0 + oyl;
             const bool valid1 = valid0 && ox + 1 < W;
             const int woff = im * PS + oyl * WS + ox;       // even: the three LDS.64 of a window row are aligned
-            // sibling `sub` drains tile `sub` (the pair's pixel ox + sub)
-            RowSink<false, DENSE, true> sink;
-            sink.scale = scale; sink.shift = shift; sink.valid = sub ? valid1 : valid0;
-            if (!DENSE) {
-                sink.obase = p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox + sub;
-                sink.tout = nullptr; sink.sCo = (unsigned)p.out[br].sC; sink.nout = p.nout;
-            } else {
-                sink.dA = p.dstA[br]; sink.dB = p.dstB[br]; sink.split = p.split[br]; sink.M = p.M[br];
-                sink.n = n0 + im; sink.HW = HW; sink.opix = oy * W + ox + sub;
-            }
+            // Epilogue: sibling `sub` drains ITS HALF of the accumulator columns of BOTH tiles, so the pair's two pixels leave as one 8-byte
+            // store per channel (a sibling that drains one tile stores every other pixel: half-used sectors, twice the store instructions)
+            float* const ob = DENSE ? nullptr
+                                    : p.out[br].base + (long long)(n0 + im) * p.out[br].sN + p.out[br].org + oy * p.out[br].Ws + ox;
+            const unsigned sCo = DENSE ? 0u : (unsigned)p.out[br].sC;
+            const long long dn = n0 + im, dpix = oy * W + ox;
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c, ++it) {
                 const uint32_t buf = it % NB;
@@ -1195,12 +1192,29 @@ tc_head2w_kernel(const __grid_constant__ HeadArgs p) {
             g.dparity ^= 1u;
             fence_after_sync();
             const int ncols = DENSE ? p.M[br] : p.nout;
+            constexpr int H0 = (NP / 16 + 1) / 2 * 16;          // columns [0, H0) -> sibling 0, [H0, NP) -> sibling 1
+            const int c_lo = sub ? H0 : 0, c_hi = min(sub ? NP : H0, ncols);
 #pragma unroll 1
-            for (int n0c = 0; n0c < ncols; n0c += 16) {
-                float d[16];
-                tmem_ld16(g.tlane + kA2Cols + sub * NP + n0c, d);
+            for (int n0c = c_lo; n0c < c_hi; n0c += 16) {
+                float d0[16], d1[16];
+                tmem_ld16(g.tlane + kA2Cols + n0c, d0);
+                tmem_ld16(g.tlane + kA2Cols + NP + n0c, d1);
                 wait_ld();
-                sink(n0c, d);
+                if (valid0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int m = n0c + j;
+                        const float v0 = fmaf(d0[j], scale[m], shift[m]), v1 = fmaf(d1[j], scale[m], shift[m]);
+                        float* dst = nullptr;
+                        if (!DENSE) { if (m < p.nout) dst = ob + (unsigned)m * sCo; }
+                        else if (m < p.split[br]) dst = p.dstA[br] + (dn * p.split[br] + m) * HW + dpix;
+                        else if (m < p.M[br]) dst = p.dstB[br] + (dn * (p.M[br] - p.split[br]) + (m - p.split[br])) * HW + dpix;
+                        if (dst) {
+                            if (valid1 && p.st2_ok) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);      // ox even: 8-byte aligned
+                            else { *dst = v0; if (valid1) dst[1] = v1; }
+                        }
+                    }
+                }
             }
         }
     }
@@ -1824,6 +1838,18 @@ static void build_lanemap(HeadArgs& a, int H, int W, int WS, int imgs, size_t PS
     a.use_map = 1;
 }
 
+static int heads_st2_ok(const HeadArgs& a, int half, int W) {
+    if (W & 1) return 0;
+    auto al8 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) == 0; };
+    if (half == 0) {
+        for (int b = 0; b < 2; ++b)
+            if (!al8(a.out[b].base) || (a.out[b].sN & 1) || (a.out[b].sC & 1) || (a.out[b].org & 1) || (a.out[b].Ws & 1)) return 0;
+        return 1;
+    }
+    for (int b = 0; b < 2; ++b) if (!al8(a.dstA[b]) || !al8(a.dstB[b])) return 0;
+    return 1;
+}
+
 int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Planes& treg, const float* const wdw[2], const float* const wpw[2],
                     float* reg, float* obj, float* cls, int A, int C, int N, cudaStream_t s) {
     if (A + C > 96 || 4 * A > 96) { set_error("tc heads: A+C=%d exceeds the output tile (96)", A + C); return YFV2_EUNSUPPORTED; }
@@ -1851,6 +1877,7 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
         const size_t PS = (size_t)(H + 4) * sIn.Ws;
         const size_t wfl = (size_t)(2 * np * 72 + 2 * np) + 72 * 28;
         const int PPI = H * ((W + 1) / 2);
+        a.st2_ok = heads_st2_ok(a, half, W);
         a.imgs = 1;
         while ((a.imgs + 1) * PPI <= 256 && a.imgs + 1 <= N &&
                (wfl + kHeadBufs * 8 * PS * (a.imgs + 1) + 4) * sizeof(float) <= kSmemCap - 1024) ++a.imgs;
@@ -1886,6 +1913,7 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
             a.dstA[0] = obj; a.dstB[0] = cls; a.split[0] = A; a.M[0] = A + C;
             a.dstA[1] = reg; a.dstB[1] = reg; a.split[1] = 4 * A; a.M[1] = 4 * A;
         }
+        a.st2_ok = heads_st2_ok(a, half, W);
         const int Wp = W / 2;
         int BR = 256 / Wp;
         if (BR > H) BR = H;
