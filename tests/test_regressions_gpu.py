@@ -111,3 +111,25 @@ def test_bucket_survives_zero_grad_set_to_none():
         assert p.grad.data_ptr() == bucket.flat[off:].data_ptr()
         off += p.numel()
     assert float(bucket.flat.abs().sum()) > 0
+
+
+def test_head_tensors_that_are_only_4_byte_aligned():
+    """The pixel-pair head kernel writes a pair as one 8-byte store when the destination allows it; caller-owned head tensors that
+    are only 4-byte aligned must take the scalar path and still come out bit-identical."""
+    import model.detector as det
+    sd = synth.make_state_dict(3)
+    m = det.Detector(80, 3, True)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = synth.make_images(4, 2, 352, 352).cuda()
+    want = [p.clone() for p in m(x)]
+    plan = m._plan_for(x)
+    odd = []
+    for p in want:                                   # same shapes, storage shifted by one float
+        flat = torch.zeros(p.numel() + 3, dtype=torch.float32, device="cuda")
+        view = flat[1:1 + p.numel()].view(p.shape)
+        assert view.data_ptr() % 8 == 4
+        odd.append(view)
+    plan.forward(x, preds=tuple(odd))
+    for a, b in zip(odd, want):
+        assert torch.equal(a, b)

@@ -15,6 +15,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:
 timeout 400 python tools/ncu_traffic.py capture gpurun_out/traffic_$T.csv > gpurun_out/traffic_$T.log 2>&1; echo "rc traffic $?"
 timeout 900 ncu --set full --clock-control none -k 'regex:^(stem|s1c_|s2c_|pw3_|tail_|tc_|decode_nms)' -s 15 -c 15 -o gpurun_out/full_$T \
     python tools/prof_fwd.py 2 > gpurun_out/ncu_full_$T.log 2>&1; echo "rc ncu full $?"
+timeout 300 python tools/nms_phases.py > gpurun_out/nms_phases_$T.json 2> gpurun_out/nms_phases_$T.err; echo "rc phases $?"
 timeout 300 python tools/bench_nms.py 10000 256 > gpurun_out/nms_$T.json 2> gpurun_out/nms_$T.err; echo "rc nms $?"
 timeout 300 python tools/bench_latency.py > gpurun_out/latency_$T.json 2> gpurun_out/latency_$T.err; echo "rc lat $?"
 YFV2_BENCH_QUICK=1 timeout 300 python bench.py --side 640 --steps 5 2> gpurun_out/bench640_$T.err | tail -1 > gpurun_out/bench640_$T.json; echo "rc 640 $?"

@@ -25,6 +25,7 @@ constexpr int kCPL = 8;              // classes per lane -> C <= 256
 constexpr int kChunkCells = 32;
 constexpr int kSStride = kChunkCells + 1;
 constexpr int kNmsChunk = 64;
+constexpr int kNmsListMinDet = 513;    // per-class kept lists pay off only for long kept lists (see sort_and_suppress)
 constexpr int kNmsListClasses = 256;   // per-class kept lists (heads + class histogram) for up to this many classes
 
 struct PostGeom {
@@ -201,6 +202,7 @@ struct NmsParams {
     double iou_thres;
     double iou_mid;    // fl32(q) > iou_thres  <=>  q > iou_mid (or >= when iou_tie_up), see iou_gt()
     float iou_mid_f;   // (float)iou_mid: a 1e-6-wide fp32 pre-test decides almost every pair without the fp64 product
+    int list_min_det;    // per-class kept lists only for max_det >= this (YFV2_NMS_LISTS=1: always, for the tests of that path)
     float iou_fast_mid;  // iou_fast(): iou_mid_f, or NaN when iou_mid <= 0 (every pair then takes the exact path)
     float iou_zero;      // iou_fast(): 0 (an empty intersection is below a positive threshold), or NaN when iou_mid <= 0
     int iou_tie_up;
@@ -231,7 +233,7 @@ struct NmsSmem {
     // `kbox` before the first box is kept, so they cost no shared memory (one more CTA per SM matters to the scoring pass)
     unsigned int* kcn;          // [max_det] low 16 bits: class of kept box, high 16: next kept box of that class (0xFFFF: end)
     unsigned short* khead;      // [kNmsListClasses] newest kept box per class
-    unsigned short* chcls;      // [2][64] classes of the staged chunks
+    unsigned short* chcls;      // [2][64] classes of the staged chunks (own storage: the padding tail of `keys` only has room for the lists)
     unsigned int* chist;        // [kNmsListClasses] candidates per class (aliases kbox; only used before the suppression loop)
     bool lists_fit;
     unsigned int* misc;         // [0]=count, [1..2]=suppressed bits, [3..4]=kept bits, [5]=some box outside (-max_wh/2, max_wh/2), [6] scratch
@@ -240,7 +242,7 @@ struct NmsSmem {
 __host__ __device__ inline size_t nms_smem_bytes(int M, int MCp, int max_det) {
     size_t b = (size_t)MCp * 8 + (size_t)M * 16 + (((size_t)M * 2 + 15) & ~(size_t)15);
     b += (size_t)max_det * 16 + (((size_t)max_det * 4 + 15) & ~(size_t)15);
-    b += 2 * kNmsChunk * 16 + 2 * kNmsChunk * 4 + kNmsChunk * 8 + kNmsChunk + 32;
+    b += 2 * kNmsChunk * 16 + 2 * kNmsChunk * 4 + kNmsChunk * 8 + kNmsChunk + 2 * kNmsChunk * 2 + 32;
     return b;
 }
 
@@ -255,11 +257,11 @@ __device__ __forceinline__ NmsSmem carve(unsigned char* base, int M, int MCp, in
     s.charea = reinterpret_cast<float*>(base); base += 2 * kNmsChunk * 4;
     s.cmask = reinterpret_cast<unsigned int*>(base); base += kNmsChunk * 8;
     s.alist = reinterpret_cast<unsigned char*>(base); base += kNmsChunk;
+    s.chcls = reinterpret_cast<unsigned short*>(base); base += 2 * kNmsChunk * 2;
     s.misc = reinterpret_cast<unsigned int*>(base);
     unsigned char* tail = reinterpret_cast<unsigned char*>(s.keys + M);
     s.kcn = reinterpret_cast<unsigned int*>(tail); tail += (size_t)max_det * 4;
     s.khead = reinterpret_cast<unsigned short*>(tail); tail += kNmsListClasses * 2;
-    s.chcls = reinterpret_cast<unsigned short*>(tail); tail += 2 * kNmsChunk * 2;
     s.lists_fit = tail <= reinterpret_cast<unsigned char*>(s.keys + MCp) && (size_t)max_det * 16 >= kNmsListClasses * 4;
     s.chist = reinterpret_cast<unsigned int*>(s.kbox);
     return s;
@@ -438,7 +440,9 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
     // ... worth it only when the candidates are spread over classes: every kept box then sits in a per-class list (newest first)
     // and a candidate walks its own class's list instead of all kept boxes.  A single dominant class (randomly initialised
     // heads: every candidate has the same arg-max) keeps the dense 4-way unrolled scan.
-    bool by_class = s.lists_fit && s.misc[5] == 0u && p.iou_mid > 0.0 && p.max_wh > 0.f && p.C <= kNmsListClasses;
+    // (since the dense scan went branch-free it is the faster one while the kept list is short -- configs[4] sets, cap 300: 2.9 / 2.5 ms
+    // per 10 000 images against 3.4 / 2.9 with the lists -- so the lists are only used for caps above kNmsListMinDet)
+    bool by_class = s.lists_fit && s.misc[5] == 0u && p.iou_mid > 0.0 && p.max_wh > 0.f && p.C <= kNmsListClasses && p.max_det >= p.list_min_det;
     if (by_class) {
         for (int i = threadIdx.x; i < kNmsListClasses; i += NT) s.chist[i] = 0u;
         if (threadIdx.x == 0) s.misc[6] = 0u;
@@ -548,25 +552,47 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
         }
         __syncthreads();
         if (t == 0) { s.misc[1] = 0u; s.misc[2] = 0u; }              // every thread has read the dead bits
-        for (int pi = t; pi < na * na; pi += NT) {
-            const int rx = pi / na, ry = pi - rx * na;
-            if (ry > rx) {
-                const int x = s.alist[rx], y = s.alist[ry];           // x earlier (higher confidence) than y
-                if (!by_class || chcls[x] == chcls[y]) {
-                    bool d, m;
-                    iou_fast(chbox[x], charea[x], chbox[y], charea[y], p, d, m);
-                    if (m) d = iou_gt(chbox[x], charea[x], chbox[y], charea[y], p);
-                    if (d) atomicOr(&s.cmask[2 * x + (y >> 5)], 1u << (y & 31));
+        if (na * na <= 4 * NT) {
+            for (int pi = t; pi < na * na; pi += NT) {
+                const int rx = pi / na, ry = pi - rx * na;
+                if (ry > rx) {
+                    const int x = s.alist[rx], y = s.alist[ry];       // x earlier (higher confidence) than y
+                    if (!by_class || chcls[x] == chcls[y]) {
+                        bool d, m;
+                        iou_fast(chbox[x], charea[x], chbox[y], charea[y], p, d, m);
+                        if (m) d = iou_gt(chbox[x], charea[x], chbox[y], charea[y], p);
+                        if (d) atomicOr(&s.cmask[2 * x + (y >> 5)], 1u << (y & 31));
+                    }
                 }
+            }
+        } else {
+            // most of the chunk survived (a) (candidates spread over many classes): ranking buys nothing, thread <-> candidate i and
+            // 16 of the later candidates, dead rows / columns and pairs of different classes skipped
+            const int i = t >> 2, jq = t & 3;
+            if ((alive >> i) & 1ull) {
+                const float4 bi = chbox[i];
+                const float ai = charea[i];
+                const unsigned short ci = by_class ? chcls[i] : (unsigned short)0;
+                unsigned int bits = 0u;
+#pragma unroll 4
+                for (int e = 0; e < 16; ++e) {
+                    const int j = jq * 16 + e;
+                    if (j > i && ((alive >> j) & 1ull) && (!by_class || chcls[j] == ci)) {
+                        bool d, m;
+                        iou_fast(bi, ai, chbox[j], charea[j], p, d, m);
+                        if (m) d = iou_gt(bi, ai, chbox[j], charea[j], p);
+                        bits |= (unsigned)d << e;
+                    }
+                }
+                if (bits) atomicOr(&s.cmask[2 * i + (jq >> 1)], bits << ((jq & 1) * 16));
             }
         }
         __syncthreads();
         tick(4);
-        // (c) greedy resolve over the kill rows, run redundantly by every thread (no hand-off barrier): the lowest live candidate is
-        // kept and its row cleared from the live set.  Two 32-bit halves keep the dependent chain short (find-first-set, one shared
-        // load, one logic op per kept candidate); a row's upper half is applied to the upper live bits off the chain.
-        unsigned long long kept;
-        {
+        // (c) greedy resolve over the kill rows by warp 0: the lowest live candidate is kept and its row cleared from the live set.  Two
+        // 32-bit halves keep the dependent chain short (find-first-set, one shared load, one logic op per kept candidate); a row's
+        // upper half is applied to the upper live bits off the chain.
+        if (t < 32) {
             unsigned int lo = (unsigned int)alive, hi = (unsigned int)(alive >> 32), klo = 0u, khi = 0u;
             int room = p.max_det - nk;
             while (lo && room > 0) {
@@ -582,8 +608,10 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
                 --room;
                 hi &= ~(1u << i) & ~s.cmask[2 * (i + 32) + 1];
             }
-            kept = ((unsigned long long)khi << 32) | (unsigned long long)klo;
+            if (t == 0) { s.misc[3] = klo; s.misc[4] = khi; }
         }
+        __syncthreads();
+        const unsigned long long kept = ((unsigned long long)s.misc[4] << 32) | (unsigned long long)s.misc[3];
         if (by_class && t == 0) {                                     // per-class lists of kept boxes, in kept order
             int pos = nk;
             for (unsigned long long r = kept; r; r &= r - 1ull, ++pos) {
@@ -634,20 +662,48 @@ nms_kernel(const float* __restrict__ dets, int C, NmsParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = 5 + C;
     const float* img = dets + (long long)n * p.M * D;
-    for (int r = warp; r < p.M; r += NT / 32) {
-        const float* row = img + (long long)r * D;
-        const float obj = __ldg(row + 4);
-        if (!(obj > p.conf_thres)) continue;                          // utils/utils.py:254 (warp uniform)
-        float best = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int c = lane; c < C; c += 32) {
-            const float v = __fmul_rn(__ldg(row + 5 + c), obj);        // :261
-            if (v > best) { best = v; bi = c; }
+    // Four rows per warp and trip: a row is one dependent round trip to DRAM (objectness, then its class scores) and the pass is
+    // bound by that latency (10 000 images: 6.2 GB in 7.8 ms = 0.8 TB/s with one row in flight per warp), so the loads of four
+    // rows are issued together.  Row order only matters through the sort key (conf, row), not through the slot a row lands in.
+    constexpr int RU = 4, NW = NT / 32;
+    for (int r0 = warp; r0 < p.M; r0 += RU * NW) {
+        const float* row[RU];
+        float obj[RU], box[RU][4];
+        bool pass[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            const int r = r0 + u * NW;
+            row[u] = img + (long long)(r < p.M ? r : r0) * D;
+            obj[u] = __ldg(row[u] + 4);
         }
-        warp_argmax(best, bi);                                        // :267 first max
-        if (lane == 0 && best > p.conf_thres && class_ok(p, bi)) {    // :268, :271-272
-            const unsigned int slot = atomicAdd(&s.misc[0], 1u);
-            write_candidate(s, slot, __ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), best, bi, r, p.max_wh);
+#pragma unroll
+        for (int u = 0; u < RU; ++u) pass[u] = (r0 + u * NW < p.M) && (obj[u] > p.conf_thres);    // utils/utils.py:254 (warp uniform)
+        float best[RU];
+        int bi[RU];
+#pragma unroll
+        for (int u = 0; u < RU; ++u) { best[u] = -INFINITY; bi[u] = 0x7fffffff; }
+        for (int c = lane; c < C; c += 32) {
+            float v[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) v[u] = pass[u] ? __ldg(row[u] + 5 + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const float w = __fmul_rn(v[u], obj[u]);               // :261
+                if (pass[u] && w > best[u]) { best[u] = w; bi[u] = c; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) box[u][k] = (pass[u] && lane == 0) ? __ldg(row[u] + k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < RU; ++u) {
+            if (!pass[u]) continue;
+            warp_argmax(best[u], bi[u]);                               // :267 first max
+            if (lane == 0 && best[u] > p.conf_thres && class_ok(p, bi[u])) {    // :268, :271-272
+                const unsigned int slot = atomicAdd(&s.misc[0], 1u);
+                write_candidate(s, slot, box[u][0], box[u][1], box[u][2], box[u][3], best[u], bi[u], r0 + u * NW, p.max_wh);
+            }
         }
     }
     sort_and_suppress<false>(s, p, n);
@@ -939,6 +995,8 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
     while (p.MCp < M) p.MCp <<= 1;
     p.C = 1 << 30;                                           // callers that know the class count set it
     p.prof = nullptr;
+    static const bool lists_always = getenv("YFV2_NMS_LISTS") != nullptr;
+    p.list_min_det = lists_always ? 0 : kNmsListMinDet;
     return YFV2_OK;
 }
 }  // namespace
