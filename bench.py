@@ -66,6 +66,59 @@ def algorithmic_bytes_per_image(H=SIDE, W=SIDE, A=ANCHORS, C=CLASSES, in_bytes=4
     return b
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_node(dev_index):
+    """Pin this process to the CPUs of ONE NUMA node before any pinned host buffer is allocated (first touch decides where its pages
+    live): the host->device feed of the e2e leg otherwise depends on which socket the scheduler happened to pick (round 1: 83 k vs
+    95 k img/s on identical code; round 2: 113 k .. 139 k).  Which node feeds the GPU fastest is MEASURED (64 MB pinned buffer first
+    touched under each node's affinity, a few timed H2D copies) rather than read from sysfs: on the round-2 boxes the node sysfs
+    calls local to the GPU was the slower one (43 vs 52 GB/s).  Returns (description, previous affinity) or (None, None)."""
+    try:
+        import glob
+        prev = os.sched_getaffinity(0)
+        nodes = []
+        for d in sorted(glob.glob("/sys/devices/system/node/node[0-9]*")):
+            cpus = _cpulist(open(d + "/cpulist").read()) & prev
+            if cpus:
+                nodes.append((os.path.basename(d), cpus))
+        if len(nodes) < 2:
+            return None, None
+        dev = torch.device("cuda", dev_index)
+        dst = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        best = None
+        for name, cpus in nodes:
+            os.sched_setaffinity(0, cpus)
+            src = torch.zeros(64 << 20, dtype=torch.uint8).pin_memory()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(6):
+                dst.copy_(src, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            gbs = 6 * (64 << 20) / (e0.elapsed_time(e1) * 1e-3) / 1e9
+            del src
+            if best is None or gbs > best[0]:
+                best = (gbs, name, cpus)
+        os.sched_setaffinity(0, best[2])
+        return "bound to NUMA %s of %d (%d cpus; measured pinned H2D %.1f GB/s, the best node)" % (best[1], len(nodes), len(best[2]), best[0]), prev
+    except Exception:
+        try:
+            os.sched_setaffinity(0, prev)
+        except Exception:
+            pass
+        return None, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -204,6 +257,7 @@ def run_ours(args, rank, world, local_rank):
     import synth
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    host_binding, prev_affinity = bind_to_gpu_node(local_rank)
     model, _ = random_state_dict()
     model = model.to(dev).eval()
     g = torch.Generator().manual_seed(1 + rank)
@@ -414,6 +468,8 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not os.environ.get("YFV2_BENCH_QUICK"):     # (QUICK: developer A/B runs only)
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)                 # the CPU baseline may use every host core
         v, info = cpu_reference_throughput(12.0, 16)
         cpu = {"value": v, "unit": "images/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]}
 
@@ -426,7 +482,8 @@ def run_ours(args, rank, world, local_rank):
                            "parallelism": "replicas x%d, no collective" % world,
                            "input": "uint8 NCHW resident in HBM, /255 fused into the stem (utils/utils.py:368)" if u8 else "fp32 NCHW resident in HBM",
                            "l2": "inputs (%d x %d MB per step, alternated) exceed the 126 MB L2; activations stream through it"
-                                 % (len(xs_dev), BATCH * 3 * SIDE * SIDE * (1 if u8 else 4) // 1000000)},
+                                 % (len(xs_dev), BATCH * 3 * SIDE * SIDE * (1 if u8 else 4) // 1000000),
+                           "host": host_binding or "no CPU binding (PCI topology not exposed)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (plan.forward_launches + 1),
                 "kept_boxes_per_step": kept, "parity_checked": parity is not None, "parity": parity, "roofline": roof, "cpu_baseline": cpu, "stages": stages}
         print(json.dumps(line), flush=True)
@@ -444,6 +501,7 @@ def run_train(args, rank, world, local_rank):
     TB = 64
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    bind_to_gpu_node(local_rank)                                         # pinned input batches next to the GPU
     torch.manual_seed(2)                                                 # same initial weights on every rank
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
