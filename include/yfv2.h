@@ -243,6 +243,12 @@ YFV2_API int yfv2_debug_gather(const yfv2_plan* plan, const void* workspace, int
 YFV2_API int yfv2_debug_pw_tc(const float* x, const float* w, float* out, float* pack_ws, int K, int N, int P,
                               void* stream);
 
+/* ---- test hook (host only, no GPU needed): the lane map the heads' pixel-pair kernel uses for an H x W map in zero frames of
+ * row stride WS / plane stride PS floats, `imgs` images per work item: out[256] = image << 16 | row << 8 | pair column, or
+ * 0xFFFFFFFF for an idle lane.  Every pair appears exactly once; the 16 lanes of a half-warp sit in different 8-byte banks
+ * wherever the geometry allows it. */
+YFV2_API int yfv2_debug_head_lanemap(int H, int W, int WS, int imgs, long long PS, unsigned int* out);
+
 /* ---- profiling hook: yfv2_decode_nms runs an instrumented kernel while dev_buf != NULL and writes, per image, 16 int64:
  * clock64 ticks of [0] candidate generation, [1] sort, [2] chunk load, [3] chunk vs kept, [4] pairs inside the chunk,
  * [5] serial resolve, [6] append, [7] tail; [8] chunks, [9] candidates, [10] kept.  dev_buf: N x 16 int64 on the device. */

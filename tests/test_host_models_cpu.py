@@ -105,3 +105,54 @@ def test_register_bitonic_network_sorts_descending():
             out, smem_steps = _sort_reg_model(keys, E)
             assert np.array_equal(out, np.sort(keys)[::-1])
             assert smem_steps == want_smem                              # log2(NT/32) * (log2(NT/32) + 1) / 2 = 6 of the steps
+
+
+def test_head_lane_map_is_a_conflict_free_permutation():
+    """Host logic of the heads' pixel-pair kernel (csrc/k_tcnet.cu:build_lanemap): every pixel pair of the item is dealt to exactly
+    one of the 256 lanes, and the 16 lanes of a half-warp read 16 different 8-byte shared-memory banks wherever a perfect deal
+    exists (22x22 at 352x352: at most two residue classes hold more than 16 pairs, so at most a few lanes double up), against
+    15 conflicted half-warps of 16 in raster order."""
+    import ctypes
+    import collections
+    import yfv2  # noqa: F401
+    import yfv2_engine
+    lib = yfv2_engine.lib()
+
+    def conflicts(entries, WS, PS):
+        extra = 0
+        for h in range(16):
+            units = collections.Counter((((e >> 16) * PS + ((e >> 8) & 0xFF) * WS + 2 * (e & 0xFF)) // 2) % 16
+                                        for e in entries[16 * h:16 * h + 16] if e != 0xFFFFFFFF)
+            extra += max(units.values()) - 1 if units else 0
+        return extra
+
+    for (H, W, WS, imgs, limit) in [(22, 22, 28, 1, 2), (20, 20, 24, 1, 0), (16, 16, 20, 2, 0), (8, 8, 12, 8, 0), (11, 11, 16, 3, 64)]:
+        PS = (H + 4) * WS
+        out = (ctypes.c_uint * 256)()
+        assert lib.yfv2_debug_head_lanemap(H, W, WS, imgs, PS, out) == 0
+        got = [e for e in out if e != 0xFFFFFFFF]
+        Wp = (W + 1) // 2
+        want = sorted((im << 16) | (r << 8) | j for im in range(imgs) for r in range(H) for j in range(Wp))
+        assert sorted(got) == want                                   # a permutation of the item's pairs
+        raster = want + [0xFFFFFFFF] * (256 - len(want))
+        assert conflicts(list(out), WS, PS) <= limit
+        if limit < 16:
+            assert conflicts(raster, WS, PS) >= 10                   # what the map removes
+    assert lib.yfv2_debug_head_lanemap(40, 40, 44, 1, 44 * 44, out) != 0        # more than 256 pairs: refused
+
+
+def test_bench_numa_binding_is_harmless_without_a_gpu():
+    """bench.bind_to_gpu_node probes pinned H2D bandwidth per NUMA node; without a usable GPU it must leave the affinity alone."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    before = os.sched_getaffinity(0)
+    desc, prev = bench.bind_to_gpu_node(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert desc is None and prev is None
+    assert os.sched_getaffinity(0) == before or desc is not None
+    if prev:
+        os.sched_setaffinity(0, prev)

@@ -1992,3 +1992,16 @@ int tc_launch_heads(int half, const Planes& sIn, const Planes& tcls, const Plane
 }
 
 }  // namespace yfv2
+
+/* test hook (host only): the lane map tc_launch_heads builds for an H x W map in frames of row stride WS and plane stride PS (floats)
+ * with `imgs` images per item: out[256] entries (image << 16 | row << 8 | pair column), 0xFFFFFFFF = idle lane. */
+extern "C" int yfv2_debug_head_lanemap(int H, int W, int WS, int imgs, long long PS, unsigned int* out) {
+    if (!out || H <= 0 || W <= 0 || H > 255 || (W + 1) / 2 > 255 || imgs <= 0 || imgs * H * ((W + 1) / 2) > 256 || (WS & 1) || (PS & 1)) {
+        yfv2::set_error("debug_head_lanemap: bad geometry");
+        return YFV2_EINVAL;
+    }
+    yfv2::HeadArgs a{};
+    yfv2::build_lanemap(a, H, W, WS, imgs, (size_t)PS);
+    memcpy(out, a.lanemap, sizeof(a.lanemap));
+    return YFV2_OK;
+}
