@@ -202,6 +202,7 @@ struct NmsParams {
     double iou_thres;
     double iou_mid;    // fl32(q) > iou_thres  <=>  q > iou_mid (or >= when iou_tie_up), see iou_gt()
     float iou_mid_f;   // (float)iou_mid: a 1e-6-wide fp32 pre-test decides almost every pair without the fp64 product
+    int sort_rolled;     // 2048-key register sort with rolled stage loops (default; YFV2_NMS_SORT_UNROLLED=1: the unrolled network)
     int list_min_det;    // per-class kept lists only for max_det >= this (YFV2_NMS_LISTS=1: always, for the tests of that path)
     float iou_fast_mid;  // iou_fast(): iou_mid_f, or NaN when iou_mid <= 0 (every pair then takes the exact path)
     float iou_zero;      // iou_fast(): 0 (an empty intersection is below a positive threshold), or NaN when iou_mid <= 0
@@ -420,6 +421,69 @@ __device__ void bitonic_sort_desc_reg(unsigned long long* keys) {
     __syncthreads();
 }
 
+// The same network with the stage loops ROLLED: the fully unrolled version above is ~4000 SASS instructions that every warp runs
+// exactly once -- ncu (profiles/r2s3_kernels_ncu.txt, source page): 58 % of the stall samples inside the sort are instruction fetch.
+// Here k and j are run-time values: strides of 32 E and more go through shared memory, strides of E and more are shuffles with a
+// run-time lane mask, strides below E are compare-exchanges inside the thread (three instantiated bodies for E = 8).  Same
+// comparisons on the same pairs in the same order: identical result.
+template <int E, int J>
+__device__ __forceinline__ void sort_intra(unsigned long long (&v)[E], int k, int t) {
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        if ((m & J) == 0) {
+            const int i = E * t + m;
+            const unsigned long long a = v[m], b = v[m | J];
+            const bool desc = (i & k) == 0;
+            if (desc ? (a < b) : (a > b)) { v[m] = b; v[m | J] = a; }
+        }
+    }
+}
+template <int E>
+__device__ void bitonic_sort_desc_reg_rolled(unsigned long long* keys) {
+    constexpr int n2 = NT * E;
+    const int t = threadIdx.x;
+    unsigned long long v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = keys[E * t + m];
+#pragma unroll 1
+    for (int k = 2; k <= n2; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= E) {
+                unsigned long long o[E];
+                const int pj = j / E;                            // partner thread t ^ pj
+                if (j >= 32 * E) {
+                    __syncthreads();                             // every earlier read of `keys` is done
+#pragma unroll
+                    for (int m = 0; m < E; ++m) keys[m * NT + t] = v[m];          // transposed: conflict-free both ways
+                    __syncthreads();
+#pragma unroll
+                    for (int m = 0; m < E; ++m) o[m] = keys[m * NT + (t ^ pj)];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) o[m] = __shfl_xor_sync(0xffffffffu, v[m], pj);
+                }
+                // element i = E t + m: bits of j and k at or above E only depend on t, so the direction is the same for all m
+                const int i0 = E * t;
+                const bool keep_max = ((i0 & k) == 0) == ((i0 & j) == 0);
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const unsigned long long a = v[m], b = o[m];
+                    v[m] = keep_max ? (a > b ? a : b) : (a < b ? a : b);
+                }
+            } else {
+                if (E > 4 && j == 4) sort_intra<E, (E > 4 ? 4 : 1)>(v, k, t);
+                else if (E > 2 && j == 2) sort_intra<E, (E > 2 ? 2 : 1)>(v, k, t);
+                else sort_intra<E, 1>(v, k, t);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < E; ++m) keys[E * t + m] = v[m];
+    __syncthreads();
+}
+
 // Sort the pushed candidates and run the blocked greedy suppression.  All threads of the CTA call this.
 // PROF (debug builds of the kernels, yfv2_debug_nms_profile): thread 0 accumulates clock64 ticks per phase; `tstart` is the
 // kernel's first timestamp.  Phases: 0 candidate generation, 1 class histogram + sort, 2 chunk load, 3 chunk vs kept, 4 pairs
@@ -457,7 +521,8 @@ __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, l
     while (n2 < cnt) n2 <<= 1;
     for (int i = cnt + threadIdx.x; i < n2; i += NT) s.keys[i] = 0ull;
     __syncthreads();
-    if (n2 == NT) bitonic_sort_desc_reg<1>(s.keys);
+    if (p.sort_rolled && n2 == 8 * NT) bitonic_sort_desc_reg_rolled<8>(s.keys);
+    else if (n2 == NT) bitonic_sort_desc_reg<1>(s.keys);
     else if (n2 == 2 * NT) bitonic_sort_desc_reg<2>(s.keys);
     else if (n2 == 4 * NT) bitonic_sort_desc_reg<4>(s.keys);
     else if (n2 == 8 * NT) bitonic_sort_desc_reg<8>(s.keys);
@@ -997,6 +1062,9 @@ int fill_nms(NmsParams& p, int M, float conf_thres, double iou_thres, const int*
     p.prof = nullptr;
     static const bool lists_always = getenv("YFV2_NMS_LISTS") != nullptr;
     p.list_min_det = lists_always ? 0 : kNmsListMinDet;
+    // default since the A/B on the bench workload (profiles/r2s3_ab_nms_sort_*.json): decode+NMS 178.8 -> 161.1 us per launch
+    static const bool sort_unrolled = getenv("YFV2_NMS_SORT_UNROLLED") != nullptr;
+    p.sort_rolled = sort_unrolled ? 0 : 1;
     return YFV2_OK;
 }
 }  // namespace
