@@ -6,8 +6,10 @@
 3. the rolled register sort derives the compare direction of a shuffle / shared-memory stage from the thread index alone.
 """
 import numpy as np
+import pytest
 
 f32 = np.float32
+pytestmark = pytest.mark.filterwarnings("ignore::RuntimeWarning")      # the degenerate cases overflow / produce NaN on purpose
 
 
 def _mid(thr):
