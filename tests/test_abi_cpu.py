@@ -99,3 +99,22 @@ def test_overlay_resolves_out_of_scope_names_from_the_reference():
     """ % os.path.join(ROOT, "yolo-fastestv2_b200"))
     r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: include/yfv2.h must compile as C99 (-pedantic) and a plain C program must link against libyfv2.so
+    and call it (yfv2_abi_version needs no GPU)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "yfv2.h"\n#include <stdio.h>\nint main(void) { printf("%d\\n", yfv2_abi_version()); return yfv2_last_error() == 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "yolo-fastestv2_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lyfv2", "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
+    assert out == "1"
