@@ -464,6 +464,13 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         stages.append(post)
+        try:        # the whole timed step against the same peak: algorithmic bytes of every launch / the step time of `value`
+            step_bytes = sum(float(s_["alg_MB"]) for s_ in stages) * 1e6
+            step_gbs = step_bytes / ((ms / args.steps) * 1e-3) / 1e9
+            roof["step"] = {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4), "algorithmic_bytes": int(step_bytes),
+                            "ms": round(ms / args.steps, 4)}
+        except Exception:
+            pass
         del flush
 
     cpu = None
