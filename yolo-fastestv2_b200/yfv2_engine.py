@@ -553,6 +553,10 @@ def ncnn_post(out2, out3, anchor_num, thresh=0.3, nms_thresh=0.25, src_size=None
     scores = torch.empty((N, max_out), dtype=torch.float32, device=dev)
     cates = torch.empty((N, max_out), dtype=torch.int32, device=dev)
     counts = torch.empty((N,), dtype=torch.int32, device=dev)
+    if len(anchors) < 4 * A:
+        raise Yfv2Error("ncnn_post: %d anchor values given, 2 levels x %d anchors x (w, h) needed" % (len(anchors), A))
+    if C <= 0:
+        raise Yfv2Error("ncnn_post: tensors with %d channels cannot hold %d anchors" % (ch, A))
     anc = (ctypes.c_float * (4 * A))(*[float(a) for a in anchors][:4 * A])
     with torch.cuda.device(dev):
         _check(lib().yfv2_ncnn_post(ctypes.c_void_p(out2.data_ptr()), ctypes.c_void_p(out3.data_ptr()), N, H, W, A, C, anc,
