@@ -250,8 +250,8 @@ YFV2_API int yfv2_debug_pw_tc(const float* x, const float* w, float* out, float*
 YFV2_API int yfv2_debug_head_lanemap(int H, int W, int WS, int imgs, long long PS, unsigned int* out);
 
 /* ---- profiling hook: yfv2_decode_nms runs an instrumented kernel while dev_buf != NULL and writes, per image, 16 int64:
- * clock64 ticks of [0] candidate generation, [1] sort, [2] chunk load, [3] chunk vs kept, [4] pairs inside the chunk,
- * [5] serial resolve, [6] append, [7] tail; [8] chunks, [9] candidates, [10] kept.  dev_buf: N x 16 int64 on the device. */
+ * clock64 ticks of [0] candidate generation, [1] sort, [2] staging of the first chunk, [3] chunk vs kept, [4] pairs inside the
+ * chunk, [5] resolve + append, [6] unused, [7] tail; [8] chunks, [9] candidates, [10] kept.  dev_buf: N x 16 int64 on the device. */
 YFV2_API int yfv2_debug_nms_profile(long long* dev_buf);
 
 #ifdef __cplusplus

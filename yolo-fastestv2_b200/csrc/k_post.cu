@@ -486,8 +486,9 @@ __device__ void bitonic_sort_desc_reg_rolled(unsigned long long* keys) {
 
 // Sort the pushed candidates and run the blocked greedy suppression.  All threads of the CTA call this.
 // PROF (debug builds of the kernels, yfv2_debug_nms_profile): thread 0 accumulates clock64 ticks per phase; `tstart` is the
-// kernel's first timestamp.  Phases: 0 candidate generation, 1 class histogram + sort, 2 chunk load, 3 chunk vs kept, 4 pairs
-// inside the chunk, 5 serial resolve, 6 append, 7 tail; [8] chunks, [9] candidates.
+// kernel's first timestamp.  Phases: 0 candidate generation, 1 class histogram + sort, 2 staging of the first chunk, 3 chunk vs
+// kept, 4 ranking + pairs inside the chunk, 5 resolve + append (+ staging of the next chunk), 6 unused, 7 tail; [8] chunks,
+// [9] candidates, [10] kept.
 template <bool PROF>
 __device__ void sort_and_suppress(const NmsSmem& s, const NmsParams& p, int n, long long tstart = 0) {
     long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
