@@ -118,3 +118,66 @@ def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
                     "-L", libdir, "-lyfv2", "-Wl,-rpath," + libdir], check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
     assert out == "1"
+
+
+def test_plan_host_logic_over_shapes():
+    """Plans are host-only objects: the launch list, the stage names and the buffer sizes must be well defined for every shape the
+    reference accepts (H, W multiples of 32, any batch) and the shape limits must be reported, not crashed on."""
+    import yfv2_engine
+    lib = yfv2_engine.lib()
+    sizes = {}
+    for (N, H, W, A, C) in [(1, 32, 32, 3, 80), (1, 352, 352, 3, 80), (256, 352, 352, 3, 80), (2, 640, 640, 3, 80), (3, 96, 160, 2, 20),
+                            (5, 224, 96, 3, 80), (1, 1024, 1024, 3, 80), (4, 352, 352, 1, 1)]:
+        h = ctypes.c_void_p()
+        assert lib.yfv2_plan_create(ctypes.byref(h), 0, N, H, W, A, C, 0) == 0, (N, H, W, A, C, lib.yfv2_last_error())
+        ws, pk, n = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_int()
+        assert lib.yfv2_plan_workspace_bytes(h, ctypes.byref(ws)) == 0 and ws.value > 0
+        assert lib.yfv2_plan_packed_bytes(h, ctypes.byref(pk)) == 0 and pk.value > 0
+        assert lib.yfv2_plan_forward_launches(h, ctypes.byref(n)) == 0 and 14 <= n.value <= 32
+        names = []
+        while True:
+            nm = lib.yfv2_plan_stage_name(h, len(names))
+            if nm is None:
+                break
+            names.append(nm.decode())
+        assert names[0] == "stem" and any(s.startswith("stage4.3") for s in names) and len(names) >= 24
+        groups = [lib.yfv2_plan_stage_group(h, i) for i in range(len(names))]
+        assert groups == sorted(groups) and groups[0] == 0 and lib.yfv2_plan_stage_group(h, len(names)) == -1
+        assert len(set(groups)) == n.value                           # one launch per group
+        sizes[(N, H, W, A, C)] = ws.value
+        assert lib.yfv2_plan_destroy(h) == 0
+    assert sizes[(256, 352, 352, 3, 80)] > 100 * sizes[(1, 352, 352, 3, 80)] // 2      # the workspace scales with the batch
+    assert sizes[(2, 640, 640, 3, 80)] > sizes[(1, 352, 352, 3, 80)]
+    h = ctypes.c_void_p()
+    for bad in [(0, 352, 352, 3, 80), (1, 352, 350, 3, 80), (1, 0, 352, 3, 80), (1, 352, 352, 0, 80), (1, 352, 352, 3, 0), (1, 352, 352, 3, 200)]:
+        rc = lib.yfv2_plan_create(ctypes.byref(h), 0, *bad, 0)
+        assert rc < 0 and lib.yfv2_last_error(), bad
+    assert lib.yfv2_plan_create(ctypes.byref(h), 0, 1, 64, 64, 3, 80, 1) < 0          # training plans are yfv2_trainer_* objects
+
+
+def test_trainer_layout_matches_the_module_parameters():
+    """The native trainer's flat gradient buffer (the bucket the data-parallel step all-reduces) is laid out on the host: its
+    offsets must be exactly the running sum of Detector.parameters() numels, for the reference shape and for others."""
+    import model.detector as det
+    import yfv2_engine
+    lib = yfv2_engine.lib()
+    lib.yfv2_trainer_destroy.restype = None
+    for (N, H, W, A, C) in [(64, 352, 352, 3, 80), (2, 64, 96, 3, 80), (3, 96, 160, 2, 20)]:
+        t = ctypes.c_void_p()
+        assert lib.yfv2_trainer_create(ctypes.byref(t), 0, N, H, W, A, C) == 0, lib.yfv2_last_error()
+        n, ws = ctypes.c_longlong(), ctypes.c_size_t()
+        assert lib.yfv2_trainer_grad_floats(t, ctypes.byref(n)) == 0
+        assert lib.yfv2_trainer_workspace_bytes(t, ctypes.byref(ws)) == 0 and ws.value > 0
+        params = list(det.Detector(C, A, True).parameters())
+        assert n.value == sum(p.numel() for p in params)
+        off = 0
+        for i, p in enumerate(params):
+            o, k = ctypes.c_longlong(), ctypes.c_longlong()
+            assert lib.yfv2_trainer_param_offset(t, i, ctypes.byref(o), ctypes.byref(k)) == 0
+            assert (o.value, k.value) == (off, p.numel()), i
+            off += p.numel()
+        o, k = ctypes.c_longlong(), ctypes.c_longlong()
+        assert lib.yfv2_trainer_param_offset(t, len(params), ctypes.byref(o), ctypes.byref(k)) < 0
+        lib.yfv2_trainer_destroy(t)
+    t = ctypes.c_void_p()
+    assert lib.yfv2_trainer_create(ctypes.byref(t), 0, 2, 100, 96, 3, 80) < 0 and lib.yfv2_last_error()
