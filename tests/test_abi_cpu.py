@@ -181,3 +181,22 @@ def test_trainer_layout_matches_the_module_parameters():
         lib.yfv2_trainer_destroy(t)
     t = ctypes.c_void_p()
     assert lib.yfv2_trainer_create(ctypes.byref(t), 0, 2, 100, 96, 3, 80) < 0 and lib.yfv2_last_error()
+
+
+def test_post_processing_entry_points_validate_before_touching_the_device():
+    """Argument errors of the decode / NMS / deploy post-process calls are reported through the return code and yfv2_last_error()
+    before anything is launched (so this runs without a GPU)."""
+    import yfv2_engine
+    lib = yfv2_engine.lib()
+    six = (ctypes.c_void_p * 6)()                                    # six null head tensors
+    anchors = (ctypes.c_double * 12)(*range(1, 13))
+    assert lib.yfv2_decode(six, 1, 352, 352, 3, 80, anchors, None, None) < 0 and lib.yfv2_last_error()
+    assert lib.yfv2_decode(six, 1, 350, 352, 3, 80, anchors, None, None) < 0 and b"32" in lib.yfv2_last_error()
+    assert lib.yfv2_decode_nms(six, 1, 352, 352, 3, 80, anchors, ctypes.c_float(0.3), ctypes.c_double(0.4), None, 0, 300,
+                               ctypes.c_float(4096.0), None, None, None, None, None) < 0
+    assert lib.yfv2_nms(None, 1, 1815, 80, ctypes.c_float(0.3), ctypes.c_double(0.4), None, 0, 300, ctypes.c_float(4096.0),
+                        None, None, None, None, None) < 0
+    fa = (ctypes.c_float * 12)(*range(1, 13))
+    assert lib.yfv2_ncnn_post(None, None, 1, 352, 352, 3, 80, fa, ctypes.c_float(0.3), ctypes.c_float(0.25), ctypes.c_float(1), ctypes.c_float(1),
+                              10, None, None, None, None, None) < 0 and b"ncnn_post" in lib.yfv2_last_error()
+    assert lib.yfv2_debug_nms_profile(None) == 0
